@@ -1,0 +1,506 @@
+// Persistent warp-specialised tcgen05 GEMM for sm_100a.
+//
+//   C[m,n] = epilogue( sum_k A[m,k] * B[n,k] ),  bf16 operands, fp32 accumulation in TMEM.
+//
+// Roles per CTA (256 threads, one CTA per SM, persistent over work units):
+//   warp 0 (1 lane) : TMA producer   global -> 128B-swizzled smem ring, mbarrier complete_tx
+//   warp 1 (1 lane) : MMA issuer     tcgen05.mma kind::f16, 128 x BN x 16 per instruction
+//   warp 2          : TMEM allocator
+//   warps 4..7      : epilogue       tcgen05.ld (32 lanes x 32 cols) -> fused epilogue -> HBM
+// Accumulators are double-buffered in TMEM (2 x BN columns) so the epilogue of tile i overlaps
+// the main loop of tile i+1.  Operands may be K-major or MN-major in memory (the "transpose"
+// of dgrad / wgrad is expressed in the UMMA descriptors, never materialised).
+//
+// Bound: tensor pipe.  Algorithmic work per launch = 2*M*N*K flop.
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+
+#include "../../include/missm_b200.h"
+#include "missm_common.cuh"
+
+namespace missm {
+
+constexpr int BM = 128;
+constexpr int BK = 64;  // 64 bf16 = one 128-byte swizzle row
+constexpr int kGemmThreads = 256;
+constexpr int A_STAGE_BYTES = BM * BK * 2;
+
+struct GemmParams {
+  int M, N, K;
+  int num_m_blk, num_n_blk, num_splits, kblk_per_split, num_kblk;
+  int a_mn, b_mn;
+  void* C;
+  int ldc;
+  const float* bias;
+  float col_scale;
+  int scale_cols;
+  const void* aux_in;
+  int ld_aux_in;
+  void* aux_out;
+  int ld_aux_out;
+  int patch_P;
+  int atomic_out;
+};
+
+template <int BN>
+struct GemmCfg {
+  static constexpr int STAGES = (BN == 256) ? 4 : 6;
+  static constexpr int B_STAGE_BYTES = BN * BK * 2;
+  static constexpr int TMEM_COLS = 2 * BN;
+  static constexpr int SMEM_BYTES = STAGES * (A_STAGE_BYTES + B_STAGE_BYTES) + 1024 /*align*/ +
+                                    256 /*barriers + tmem slot*/;
+};
+
+// ---------------------------------------------------------------------------------------
+// epilogue for one row x 32 consecutive columns held in registers
+// ---------------------------------------------------------------------------------------
+template <int EPI, bool OUT_F32>
+__device__ __forceinline__ void epilogue_row32(const GemmParams& p, int row, int col0,
+                                               const uint32_t (&acc)[32]) {
+  const int ncols = min(32, p.N - col0);  // N % 8 == 0 is enforced by the host
+  float v[32];
+#pragma unroll
+  for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(acc[j]);
+
+  if (p.bias != nullptr) {
+#pragma unroll
+    for (int j = 0; j < 32; j += 4) {
+      if (j < ncols) {
+        float4 b = __ldg(reinterpret_cast<const float4*>(p.bias + col0 + j));
+        v[j] += b.x, v[j + 1] += b.y, v[j + 2] += b.z, v[j + 3] += b.w;
+      }
+    }
+  }
+
+  size_t out_row = static_cast<size_t>(row);
+  if constexpr (EPI == MISSM_EPI_LINEAR) {
+    if (p.scale_cols > 0) {
+#pragma unroll
+      for (int j = 0; j < 32; ++j)
+        if (col0 + j < p.scale_cols) v[j] *= p.col_scale;
+    }
+  } else if constexpr (EPI == MISSM_EPI_GELU) {
+    __nv_bfloat16* u = reinterpret_cast<__nv_bfloat16*>(p.aux_out) +
+                       static_cast<size_t>(row) * p.ld_aux_out + col0;
+#pragma unroll
+    for (int j = 0; j < 32; j += 8) {
+      if (j < ncols) {
+        uint4 q;
+        q.x = pack_bf16x2(v[j], v[j + 1]);
+        q.y = pack_bf16x2(v[j + 2], v[j + 3]);
+        q.z = pack_bf16x2(v[j + 4], v[j + 5]);
+        q.w = pack_bf16x2(v[j + 6], v[j + 7]);
+        *reinterpret_cast<uint4*>(u + j) = q;
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < 32; ++j) v[j] = quick_gelu(v[j]);
+  } else if constexpr (EPI == MISSM_EPI_RESID) {
+    const float* r = reinterpret_cast<const float*>(p.aux_in) +
+                     static_cast<size_t>(row) * p.ld_aux_in + col0;
+#pragma unroll
+    for (int j = 0; j < 32; j += 4) {
+      if (j < ncols) {
+        float4 x = *reinterpret_cast<const float4*>(r + j);
+        v[j] += x.x, v[j + 1] += x.y, v[j + 2] += x.z, v[j + 3] += x.w;
+      }
+    }
+  } else if constexpr (EPI == MISSM_EPI_DGELU) {
+    const __nv_bfloat16* u = reinterpret_cast<const __nv_bfloat16*>(p.aux_in) +
+                             static_cast<size_t>(row) * p.ld_aux_in + col0;
+#pragma unroll
+    for (int j = 0; j < 32; j += 8) {
+      if (j < ncols) {
+        uint4 q = *reinterpret_cast<const uint4*>(u + j);
+        float2 a = unpack_bf16x2(q.x), b = unpack_bf16x2(q.y), c = unpack_bf16x2(q.z),
+               d = unpack_bf16x2(q.w);
+        v[j] *= quick_gelu_grad(a.x), v[j + 1] *= quick_gelu_grad(a.y);
+        v[j + 2] *= quick_gelu_grad(b.x), v[j + 3] *= quick_gelu_grad(b.y);
+        v[j + 4] *= quick_gelu_grad(c.x), v[j + 5] *= quick_gelu_grad(c.y);
+        v[j + 6] *= quick_gelu_grad(d.x), v[j + 7] *= quick_gelu_grad(d.y);
+      }
+    }
+  } else if constexpr (EPI == MISSM_EPI_PATCH) {
+    const int sample = row / p.patch_P, patch = row % p.patch_P;
+    out_row = static_cast<size_t>(sample) * (p.patch_P + 1) + 1 + patch;
+    const float* pos = reinterpret_cast<const float*>(p.aux_in) +
+                       static_cast<size_t>(1 + patch) * p.ld_aux_in + col0;
+#pragma unroll
+    for (int j = 0; j < 32; j += 4) {
+      if (j < ncols) {
+        float4 x = __ldg(reinterpret_cast<const float4*>(pos + j));
+        v[j] += x.x, v[j + 1] += x.y, v[j + 2] += x.z, v[j + 3] += x.w;
+      }
+    }
+  }
+
+  if constexpr (OUT_F32) {
+    float* c = reinterpret_cast<float*>(p.C) + out_row * p.ldc + col0;
+    if (p.atomic_out) {
+#pragma unroll
+      for (int j = 0; j < 32; j += 4) {
+        if (j < ncols) {
+          asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(c + j), "f"(v[j]),
+                       "f"(v[j + 1]), "f"(v[j + 2]), "f"(v[j + 3])
+                       : "memory");
+        }
+      }
+    } else {
+#pragma unroll
+      for (int j = 0; j < 32; j += 4) {
+        if (j < ncols)
+          *reinterpret_cast<float4*>(c + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+      }
+    }
+  } else {
+    __nv_bfloat16* c = reinterpret_cast<__nv_bfloat16*>(p.C) + out_row * p.ldc + col0;
+#pragma unroll
+    for (int j = 0; j < 32; j += 8) {
+      if (j < ncols) {
+        uint4 q;
+        q.x = pack_bf16x2(v[j], v[j + 1]);
+        q.y = pack_bf16x2(v[j + 2], v[j + 3]);
+        q.z = pack_bf16x2(v[j + 4], v[j + 5]);
+        q.w = pack_bf16x2(v[j + 6], v[j + 7]);
+        *reinterpret_cast<uint4*>(c + j) = q;
+      }
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------
+// kernel
+// ---------------------------------------------------------------------------------------
+template <int BN, int EPI, bool OUT_F32>
+__global__ void __launch_bounds__(kGemmThreads, 1)
+gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA,
+                    const __grid_constant__ CUtensorMap tmB, const GemmParams p) {
+  using Cfg = GemmCfg<BN>;
+  constexpr int STAGES = Cfg::STAGES;
+  constexpr int B_STAGE_BYTES = Cfg::B_STAGE_BYTES;
+
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>(
+      (reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
+  uint8_t* sA = smem;
+  uint8_t* sB = smem + STAGES * A_STAGE_BYTES;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(sB + STAGES * B_STAGE_BYTES);
+  uint64_t* empty_bar = full_bar + STAGES;
+  uint64_t* tfull_bar = empty_bar + STAGES;
+  uint64_t* tempty_bar = tfull_bar + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int i = 0; i < STAGES; ++i) {
+      mbar_init(&full_bar[i], 1);
+      mbar_init(&empty_bar[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&tfull_bar[i], 1);
+      mbar_init(&tempty_bar[i], 4);  // one arrive per epilogue warp
+    }
+    fence_mbar_init();
+  }
+  if (warp == 2) {
+    tmem_alloc(tmem_slot, Cfg::TMEM_COLS);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  const int tiles_mn = p.num_m_blk * p.num_n_blk;
+  const int total_work = tiles_mn * p.num_splits;
+
+  if (warp == 0) {
+    // ================================ TMA producer ====================================
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int w = blockIdx.x; w < total_work; w += gridDim.x) {
+        const int split = w / tiles_mn, rem = w % tiles_mn;
+        const int n_blk = rem / p.num_m_blk, m_blk = rem % p.num_m_blk;
+        const int kb0 = split * p.kblk_per_split;
+        const int kb1 = min(kb0 + p.kblk_per_split, p.num_kblk);
+        for (int kb = kb0; kb < kb1; ++kb) {
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          mbar_arrive_expect_tx(&full_bar[stage], A_STAGE_BYTES + B_STAGE_BYTES);
+          uint8_t* a_dst = sA + stage * A_STAGE_BYTES;
+          uint8_t* b_dst = sB + stage * B_STAGE_BYTES;
+          if (!p.a_mn) {
+            tma_load_2d(a_dst, &tmA, &full_bar[stage], kb * BK, m_blk * BM);
+          } else {
+#pragma unroll
+            for (int j = 0; j < BM / 64; ++j)
+              tma_load_2d(a_dst + j * (BK * 128), &tmA, &full_bar[stage], m_blk * BM + j * 64,
+                          kb * BK);
+          }
+          if (!p.b_mn) {
+            tma_load_2d(b_dst, &tmB, &full_bar[stage], kb * BK, n_blk * BN);
+          } else {
+#pragma unroll
+            for (int j = 0; j < BN / 64; ++j)
+              tma_load_2d(b_dst + j * (BK * 128), &tmB, &full_bar[stage], n_blk * BN + j * 64,
+                          kb * BK);
+          }
+          if (++stage == STAGES) stage = 0, phase ^= 1;
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ================================ MMA issuer ======================================
+    if (lane == 0) {
+      const uint32_t idesc = umma_idesc_bf16_f32(BM, BN, p.a_mn, p.b_mn);
+      // K-major SW128: rows of 128 B, 8-row groups 1024 B apart (SBO); K step of 16 = +32 B.
+      // MN-major SW128: 64-element MN chunks (BK rows x 128 B) LBO apart, 8-k-row groups 1024 B
+      // apart (SBO); K step of 16 = +16 rows = +2048 B.
+      const uint32_t a_lbo = p.a_mn ? BK * 128 : 16, b_lbo = p.b_mn ? BK * 128 : 16;
+      const uint32_t a_kstep = p.a_mn ? 2048 : 32, b_kstep = p.b_mn ? 2048 : 32;
+      int stage = 0;
+      uint32_t phase = 0;
+      int acc = 0;
+      uint32_t acc_phase = 0;
+      for (int w = blockIdx.x; w < total_work; w += gridDim.x) {
+        const int split = w / tiles_mn;
+        const int kb0 = split * p.kblk_per_split;
+        const int kb1 = min(kb0 + p.kblk_per_split, p.num_kblk);
+        mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * BN;
+        for (int kb = kb0; kb < kb1; ++kb) {
+          mbar_wait(&full_bar[stage], phase);
+          tc_fence_after();
+          const uint32_t a_base = smem_u32(sA + stage * A_STAGE_BYTES);
+          const uint32_t b_base = smem_u32(sB + stage * B_STAGE_BYTES);
+#pragma unroll
+          for (int k = 0; k < BK / 16; ++k) {
+            const uint64_t a_desc = umma_smem_desc_sw128(a_base + k * a_kstep, a_lbo, 1024);
+            const uint64_t b_desc = umma_smem_desc_sw128(b_base + k * b_kstep, b_lbo, 1024);
+            umma_f16_ss(d_tmem, a_desc, b_desc, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+          }
+          umma_commit(&empty_bar[stage]);  // frees the smem slot once these MMAs retire
+          if (++stage == STAGES) stage = 0, phase ^= 1;
+        }
+        umma_commit(&tfull_bar[acc]);  // accumulator complete -> epilogue
+        if (++acc == 2) acc = 0, acc_phase ^= 1;
+      }
+    }
+  } else if (warp >= 4) {
+    // ================================ epilogue ========================================
+    const int q = warp & 3;  // TMEM lane quarter this warp may access
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int w = blockIdx.x; w < total_work; w += gridDim.x) {
+      const int rem = w % tiles_mn;
+      const int n_blk = rem / p.num_m_blk, m_blk = rem % p.num_m_blk;
+      mbar_wait(&tfull_bar[acc], acc_phase);
+      tc_fence_after();
+      const int row = m_blk * BM + q * 32 + lane;
+      const uint32_t t_row = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * BN;
+#pragma unroll 1
+      for (int c = 0; c < BN / 32; ++c) {
+        const int col0 = n_blk * BN + c * 32;
+        if (col0 >= p.N) break;  // warp-uniform
+        uint32_t r[32];
+        tmem_ld_32x32b_x32(t_row + c * 32, r);
+        tmem_ld_wait();
+        if (row < p.M) epilogue_row32<EPI, OUT_F32>(p, row, col0, r);
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tempty_bar[acc]);
+      if (++acc == 2) acc = 0, acc_phase ^= 1;
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
+  }
+}
+
+// ---------------------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------------------
+static thread_local char g_last_error[512] = "";
+
+void set_last_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_last_error, sizeof(g_last_error), fmt, ap);
+  va_end(ap);
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*,
+                                  const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                  const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  if (fn) return fn;
+  void* p = nullptr;
+  cudaDriverEntryPointQueryResult qres;
+  if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) !=
+          cudaSuccess ||
+      qres != cudaDriverEntryPointSuccess || p == nullptr)
+    return nullptr;
+  fn = reinterpret_cast<EncodeTiledFn>(p);
+  return fn;
+}
+
+int make_tmap_2d_bf16(CUtensorMap* out, const void* base, uint64_t inner, uint64_t outer,
+                      uint64_t ld_elems, uint32_t box_inner, uint32_t box_outer) {
+  EncodeTiledFn fn = get_encode_fn();
+  MISSM_REQUIRE(fn != nullptr, "cuTensorMapEncodeTiled entry point unavailable");
+  MISSM_REQUIRE((reinterpret_cast<uintptr_t>(base) & 15) == 0, "TMA base not 16B aligned");
+  MISSM_REQUIRE((ld_elems * 2) % 16 == 0, "TMA row pitch (%llu elems) not a multiple of 16 B",
+                (unsigned long long)ld_elems);
+  cuuint64_t gdim[2] = {inner, outer};
+  cuuint64_t gstride[1] = {ld_elems * 2};
+  cuuint32_t box[2] = {box_inner, box_outer};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), gdim,
+                  gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                  CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  MISSM_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled failed with %d", (int)r);
+  return 0;
+}
+
+template <int BN, int EPI, bool OUT_F32>
+static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmParams& p,
+                       int grid, cudaStream_t stream) {
+  using Cfg = GemmCfg<BN>;
+  auto kern = gemm_tcgen05_kernel<BN, EPI, OUT_F32>;
+  static bool configured = false;  // benign race: the attribute call is idempotent
+  if (!configured) {
+    MISSM_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                          Cfg::SMEM_BYTES));
+    configured = true;
+  }
+  kern<<<grid, kGemmThreads, Cfg::SMEM_BYTES, stream>>>(tmA, tmB, p);
+  MISSM_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+template <int BN>
+static int dispatch_epi(int epi, bool out_f32, const CUtensorMap& a, const CUtensorMap& b,
+                        const GemmParams& p, int grid, cudaStream_t s) {
+  switch (epi) {
+    case MISSM_EPI_LINEAR:
+      return out_f32 ? launch_gemm<BN, MISSM_EPI_LINEAR, true>(a, b, p, grid, s)
+                     : launch_gemm<BN, MISSM_EPI_LINEAR, false>(a, b, p, grid, s);
+    case MISSM_EPI_GELU:
+      MISSM_REQUIRE(!out_f32, "GELU epilogue writes bf16");
+      return launch_gemm<BN, MISSM_EPI_GELU, false>(a, b, p, grid, s);
+    case MISSM_EPI_RESID:
+      MISSM_REQUIRE(out_f32, "RESID epilogue writes f32");
+      return launch_gemm<BN, MISSM_EPI_RESID, true>(a, b, p, grid, s);
+    case MISSM_EPI_DGELU:
+      MISSM_REQUIRE(!out_f32, "DGELU epilogue writes bf16");
+      return launch_gemm<BN, MISSM_EPI_DGELU, false>(a, b, p, grid, s);
+    case MISSM_EPI_PATCH:
+      MISSM_REQUIRE(out_f32, "PATCH epilogue writes f32");
+      return launch_gemm<BN, MISSM_EPI_PATCH, true>(a, b, p, grid, s);
+  }
+  MISSM_REQUIRE(false, "unknown epilogue %d", epi);
+}
+
+}  // namespace missm
+
+using namespace missm;
+
+extern "C" int missm_version(void) { return MISSM_ABI_VERSION; }
+extern "C" const char* missm_last_error(void) { return g_last_error; }
+
+extern "C" int missm_gemm_bf16(const missm_gemm_args* a, void* stream_v) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_v);
+  MISSM_REQUIRE(a != nullptr, "null args");
+  MISSM_REQUIRE(a->M >= 0 && a->N > 0 && a->K > 0, "bad dims M=%d N=%d K=%d", a->M, a->N, a->K);
+  if (a->M == 0) return 0;
+  MISSM_REQUIRE(a->N % 8 == 0, "N=%d must be a multiple of 8", a->N);
+  MISSM_REQUIRE(a->ldc % 4 == 0, "ldc=%d must be a multiple of 4", a->ldc);
+  MISSM_REQUIRE(a->A && a->B && a->C, "null operand");
+  const int epi = a->epilogue;
+  if (epi == MISSM_EPI_GELU) MISSM_REQUIRE(a->aux_out != nullptr, "GELU needs aux_out");
+  if (epi == MISSM_EPI_RESID || epi == MISSM_EPI_DGELU || epi == MISSM_EPI_PATCH)
+    MISSM_REQUIRE(a->aux_in != nullptr, "epilogue %d needs aux_in", epi);
+  if (epi == MISSM_EPI_PATCH) MISSM_REQUIRE(a->patch_P > 0, "PATCH needs patch_P");
+
+  GemmParams p;
+  memset(&p, 0, sizeof(p));
+  p.M = a->M, p.N = a->N, p.K = a->K;
+  p.a_mn = a->a_mn ? 1 : 0, p.b_mn = a->b_mn ? 1 : 0;
+  p.C = a->C, p.ldc = a->ldc, p.bias = a->bias;
+  p.col_scale = a->col_scale, p.scale_cols = a->scale_cols;
+  p.aux_in = a->aux_in, p.ld_aux_in = a->ld_aux_in;
+  p.aux_out = a->aux_out, p.ld_aux_out = a->ld_aux_out;
+  p.patch_P = a->patch_P;
+  p.num_m_blk = (a->M + BM - 1) / BM;
+  p.num_kblk = (a->K + BK - 1) / BK;
+
+  // tile-N: pick the shape that wastes fewer SM-waves (148 persistent CTAs)
+  auto waves_eff = [&](int bn) {
+    long tiles = static_cast<long>(p.num_m_blk) * ((a->N + bn - 1) / bn);
+    long waves = (tiles + kNumSMs - 1) / kNumSMs;
+    return static_cast<double>(tiles) * bn / (static_cast<double>(waves) * kNumSMs * 256.0);
+  };
+  int bn = 256;
+  if (a->force_bn == 128 || a->force_bn == 256)
+    bn = a->force_bn;
+  else if (a->N <= 128 || waves_eff(128) > 1.10 * waves_eff(256))
+    bn = 128;
+  p.num_n_blk = (a->N + bn - 1) / bn;
+
+  // split-K (atomic fp32 accumulation) when the output grid cannot fill the machine
+  const long tiles = static_cast<long>(p.num_m_blk) * p.num_n_blk;
+  int splits = 1;
+  const bool may_split = (epi == MISSM_EPI_LINEAR && a->out_f32 && a->bias == nullptr &&
+                          a->scale_cols == 0 && a->split_k != 1);
+  if (may_split) {
+    if (a->split_k > 1) {
+      splits = a->split_k;
+    } else if (tiles * 2 <= kNumSMs && p.num_kblk >= 16) {
+      splits = static_cast<int>((2L * kNumSMs + tiles - 1) / tiles);
+      if (splits > p.num_kblk / 8) splits = p.num_kblk / 8;
+    }
+    if (splits > p.num_kblk) splits = p.num_kblk;
+    if (splits < 1) splits = 1;
+  }
+  p.kblk_per_split = (p.num_kblk + splits - 1) / splits;
+  p.num_splits = (p.num_kblk + p.kblk_per_split - 1) / p.kblk_per_split;
+  p.atomic_out = p.num_splits > 1 ? 1 : 0;
+  if (p.atomic_out) {
+    MISSM_CHECK_CUDA(cudaMemset2DAsync(a->C, static_cast<size_t>(a->ldc) * 4, 0,
+                                       static_cast<size_t>(a->N) * 4, a->M, stream));
+  }
+
+  CUtensorMap tmA, tmB;
+  int rc;
+  if (!p.a_mn)
+    rc = make_tmap_2d_bf16(&tmA, a->A, a->K, a->M, a->lda, BK, BM);
+  else
+    rc = make_tmap_2d_bf16(&tmA, a->A, a->M, a->K, a->lda, 64, BK);
+  if (rc) return rc;
+  if (!p.b_mn)
+    rc = make_tmap_2d_bf16(&tmB, a->B, a->K, a->N, a->ldb, BK, bn);
+  else
+    rc = make_tmap_2d_bf16(&tmB, a->B, a->N, a->K, a->ldb, 64, BK);
+  if (rc) return rc;
+
+  const long work = tiles * p.num_splits;
+  const int grid = static_cast<int>(work < kNumSMs ? work : kNumSMs);
+  if (bn == 256) return dispatch_epi<256>(epi, a->out_f32 != 0, tmA, tmB, p, grid, stream);
+  return dispatch_epi<128>(epi, a->out_f32 != 0, tmA, tmB, p, grid, stream);
+}

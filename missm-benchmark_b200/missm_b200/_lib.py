@@ -1,0 +1,74 @@
+"""ctypes binding of the C-ABI library `lib/libmissm_b200.so` (declared in include/missm_b200.h).
+
+The product path has NO fallback: if the library is missing or a call fails, a RuntimeError is
+raised.  `import torch` happens first so that the already-loaded libcudart.so.12 is shared.
+"""
+import ctypes
+import os
+
+import torch  # noqa: F401  (loads libcudart into the process before our library)
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(os.path.dirname(_HERE), "lib", "libmissm_b200.so")
+
+c_void_p = ctypes.c_void_p
+c_int = ctypes.c_int32
+c_float = ctypes.c_float
+
+
+class GemmArgs(ctypes.Structure):
+    """Mirror of `missm_gemm_args` (include/missm_b200.h)."""
+    _fields_ = [
+        ("A", c_void_p), ("B", c_void_p), ("C", c_void_p),
+        ("bias", c_void_p), ("aux_in", c_void_p), ("aux_out", c_void_p),
+        ("M", c_int), ("N", c_int), ("K", c_int),
+        ("lda", c_int), ("ldb", c_int), ("ldc", c_int),
+        ("ld_aux_in", c_int), ("ld_aux_out", c_int),
+        ("a_mn", c_int), ("b_mn", c_int),
+        ("epilogue", c_int), ("out_f32", c_int),
+        ("scale_cols", c_int), ("col_scale", c_float),
+        ("patch_P", c_int), ("split_k", c_int), ("force_bn", c_int),
+    ]
+
+
+_lib = None
+
+
+def lib():
+    """Load (once) and return the ctypes handle; raises if the CUDA library is not built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise RuntimeError(
+            f"missm_b200: {LIB_PATH} not found. Build it with `python -c 'import __graft_entry__ "
+            f"as g; g.build()'` (or `make -C missm-benchmark_b200/csrc`). There is no CPU fallback.")
+    L = ctypes.CDLL(LIB_PATH)
+    L.missm_version.restype = c_int
+    L.missm_last_error.restype = ctypes.c_char_p
+    _declare(L)
+    _lib = L
+    return L
+
+
+def _declare(L):
+    from . import _abi
+    for name, argtypes in _abi.SIGNATURES.items():
+        fn = getattr(L, name)
+        fn.restype = c_int
+        fn.argtypes = argtypes
+
+
+def check(rc, what=""):
+    if rc != 0:
+        msg = lib().missm_last_error().decode("utf-8", "replace")
+        raise RuntimeError(f"missm_b200 {what} failed (rc={rc}): {msg}")
+
+
+def stream_ptr():
+    """Raw cudaStream_t of torch's current stream (0 = legacy default stream)."""
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def ptr(t):
+    return ctypes.c_void_p(t.data_ptr()) if t is not None else ctypes.c_void_p(0)
