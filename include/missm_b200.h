@@ -71,6 +71,113 @@ typedef struct missm_gemm_args {
 
 int missm_gemm_bf16(const missm_gemm_args* args, void* stream);
 
+/* ---------------------------------------------------------------------------------------
+ * Fused attention (head_dim 64).  Replaces transformers 4.3x CLIPAttention's score/softmax/
+ * value chain, called at languagebind/image/modeling_image.py:121 (temporal) and :140 (spatial;
+ * text adds the causal mask of :441-455 and the padding mask of :500-502).
+ * Sequence s, token t lives at row
+ *     (s / s_in) * seq_outer + (s % s_in) * seq_inner + t * tok_stride
+ * of qkv [rows, ld_qkv] (q | k | v column blocks of width D, q pre-scaled) and of out/d_out
+ * [rows, ld_o].  key_mask (int64, 1 = attend, [*, N]) row = mask_rows ? mask_rows[s / mask_div]
+ * : s / mask_div.  lse / delta: float [n_seq, H, N].
+ * ------------------------------------------------------------------------------------- */
+typedef struct missm_attn_args {
+  const void* qkv;
+  void* out;
+  float* lse;
+  const void* d_out; /* bwd */
+  float* delta;      /* bwd workspace */
+  void* dqkv;        /* bwd out, same layout as qkv */
+  const int64_t* key_mask;
+  const int32_t* mask_rows;
+  int64_t ld_qkv, ld_o;
+  int64_t seq_outer, seq_inner, tok_stride;
+  int32_t D, H, N, head_dim;
+  int32_t n_seq, s_in;
+  int32_t causal, mask_div;
+  float q_scale; /* bwd: dq is multiplied by this */
+} missm_attn_args;
+
+int missm_attention_fwd(const missm_attn_args* args, void* stream);
+int missm_attention_bwd(const missm_attn_args* args, void* stream);
+
+/* ---------------------------------------------------------------------------------------
+ * LayerNorm over rows of the fp32 residual stream (nn.LayerNorm at modeling_image.py:120,132,
+ * 139,149,649,660,514 and src/model/baseline.py:61).  Row r reads x[(row_index ? row_index[r]
+ * : r) * ldx].  Optional add_rows: x <- x + add_rows[(r / add_div) % add_period] first (the
+ * temporal embedding of modeling_image.py:110-114), written back to x_out.
+ * ------------------------------------------------------------------------------------- */
+int missm_layernorm_fwd(const float* x, int64_t ldx, const int32_t* row_index,
+                        const float* add_rows, int32_t add_period, int32_t add_div, float* x_out,
+                        const float* gamma, const float* beta, void* y, int64_t ldy, int32_t y_bf16,
+                        float* mean, float* rstd, int32_t M, int32_t D, float eps, void* stream);
+int missm_ln_bwd_num_partials(int32_t M);
+/* dx[row_index? row_index[r] : r] = (dres ? dres : 0) + LN'(dy); partial = workspace of
+ * missm_ln_bwd_num_partials(M) * 2 * D floats; dgamma, dbeta = [D]. */
+int missm_layernorm_bwd(const void* dy, int64_t lddy, int32_t dy_bf16, const float* x, int64_t ldx,
+                        const int32_t* row_index, const float* mean, const float* rstd,
+                        const float* gamma, const float* dres, float* dx, void* dx_bf16,
+                        float* partial, float* dgamma, float* dbeta, int32_t M, int32_t D,
+                        void* stream);
+int missm_reduce_partials(const float* partial, int32_t R, int64_t stride, float* out, int32_t n,
+                          float scale, void* stream);
+
+/* ---------------------------------------------------------------------------------------
+ * HBM-bound helpers
+ * ------------------------------------------------------------------------------------- */
+/* weights fp32 -> bf16 operand copies (dst may be wider: zero padded to cols_dst) */
+int missm_cast_f32_bf16(const float* src, int64_t ld_src, void* dst, int64_t ld_dst, int32_t rows,
+                        int32_t cols, int32_t cols_dst, void* stream);
+/* bias gradients: out[n] = sum_m x[m, n]  (x bf16); partial = [missm_colsum_num_partials(M), N] */
+int missm_colsum_num_partials(int32_t M);
+int missm_colsum_bf16(const void* x, int64_t ldx, int32_t M, int32_t N, float* partial, float* out,
+                      void* stream);
+/* Conv2d(k = stride = ps, no bias) input patches (video/modeling_video.py:29-35,45):
+ * pixels f32 [*, C, H, W] (sample b read from sample_index ? sample_index[b] : b)
+ * -> bf16 [Bn * (H/ps) * (W/ps), Kpad], column (c*ps + i)*ps + j, zero padded */
+int missm_patchify(const float* pixels, const int32_t* sample_index, void* patches, int32_t Bn,
+                   int32_t C, int32_t H, int32_t W, int32_t ps, int32_t Kpad, void* stream);
+/* tok[b, 0, :] = class_embedding + position_embedding[0]   (modeling_video.py:48-50) */
+int missm_cls_rows(const float* cls, const float* pos, float* tok, int32_t Bn, int32_t ntok, int32_t D,
+                   void* stream);
+/* dpos[t] = sum_b dtok[b, t]; dpatch_bf16[b*(ntok-1) + t-1] = dtok[b, t] for t >= 1 */
+int missm_embed_bwd(const float* dtok, float* dpos, void* dpatch_bf16, int32_t Bn, int32_t ntok,
+                    int32_t D, void* stream);
+/* pooled.reshape(B, T, -1).mean(1)   (modeling_image.py:662) */
+int missm_frame_mean(const float* in, void* out, int32_t out_bf16, int32_t Bn, int32_t T, int32_t D,
+                     void* stream);
+int missm_frame_mean_bwd(const float* dout, float* din, int32_t Bn, int32_t T, int32_t D, void* stream);
+/* value / value.norm(p=2, dim=-1) * exp(logit_scale)   (languagebind/__init__.py:80-83) */
+int missm_l2norm_scale_fwd(const float* x, float* y, float* inv_norm, float scale, int32_t Bn,
+                           int32_t P, void* stream);
+int missm_l2norm_scale_bwd(const float* dy, const float* x, const float* inv_norm, float scale,
+                           void* dx, int32_t dx_bf16, int32_t Bn, int32_t P, void* stream);
+/* transformers 4.3x CLIPTextEmbeddings (modeling_image.py:463,494) and the EOT pooling index
+ * (modeling_image.py:519-522: argmax of int32-cast ids, first maximum) */
+int missm_text_embed_fwd(const int64_t* ids, const int32_t* sample_index, const float* tok_emb,
+                         const float* pos_emb, float* out, int32_t Bn, int32_t L, int32_t D,
+                         void* stream);
+int missm_text_embed_bwd(const int64_t* ids, const int32_t* sample_index, const float* dx,
+                         float* dtok_emb, float* dpos, int32_t Bn, int32_t L, int32_t D, void* stream);
+int missm_argmax_rows(const int64_t* ids, const int32_t* sample_index, int32_t* out_rows, int32_t Bn,
+                      int32_t L, void* stream);
+
+/* ---------------------------------------------------------------------------------------
+ * Missing-modality mask compaction (mask of src/model/baseline.py:57).
+ * For tower i: present_idx[i, 0:counts[i]] = ascending { b : missing_index[b] != codes[i] },
+ * slot_of[i, b] = position of b in that list or -1.  codes_host is a HOST array.
+ * ------------------------------------------------------------------------------------- */
+#define MISSM_MAX_TOWERS 8
+int missm_compact_mask(const int64_t* missing_index, int32_t Bn, const int32_t* codes_host,
+                       int32_t n_towers, int32_t* present_idx, int32_t* slot_of, int32_t* counts,
+                       void* stream);
+/* dst[b] = slot_of[b] >= 0 ? src[slot_of[b]] : 0   (f32 rows of P) */
+int missm_scatter_rows_zero(const float* src, const int32_t* slot_of, float* dst, int32_t Bn,
+                            int32_t P, void* stream);
+/* dst[r] = src[idx[r]]   (rows of row_bytes bytes, multiple of 16) */
+int missm_gather_rows(const void* src, const int32_t* idx, void* dst, int32_t n_rows,
+                      int64_t row_bytes, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

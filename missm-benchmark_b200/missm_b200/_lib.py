@@ -16,6 +16,21 @@ c_int = ctypes.c_int32
 c_float = ctypes.c_float
 
 
+class AttnArgs(ctypes.Structure):
+    """Mirror of `missm_attn_args` (include/missm_b200.h)."""
+    _fields_ = [
+        ("qkv", ctypes.c_void_p), ("out", ctypes.c_void_p), ("lse", ctypes.c_void_p),
+        ("d_out", ctypes.c_void_p), ("delta", ctypes.c_void_p), ("dqkv", ctypes.c_void_p),
+        ("key_mask", ctypes.c_void_p), ("mask_rows", ctypes.c_void_p),
+        ("ld_qkv", ctypes.c_int64), ("ld_o", ctypes.c_int64),
+        ("seq_outer", ctypes.c_int64), ("seq_inner", ctypes.c_int64), ("tok_stride", ctypes.c_int64),
+        ("D", ctypes.c_int32), ("H", ctypes.c_int32), ("N", ctypes.c_int32), ("head_dim", ctypes.c_int32),
+        ("n_seq", ctypes.c_int32), ("s_in", ctypes.c_int32),
+        ("causal", ctypes.c_int32), ("mask_div", ctypes.c_int32),
+        ("q_scale", ctypes.c_float),
+    ]
+
+
 class GemmArgs(ctypes.Structure):
     """Mirror of `missm_gemm_args` (include/missm_b200.h)."""
     _fields_ = [

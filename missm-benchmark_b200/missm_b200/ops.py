@@ -1,13 +1,21 @@
-"""Thin Python wrappers over the C ABI: shape/dtype validation happens here, in Python, and the
-CUDA entry points receive raw device pointers + the current stream."""
+"""Thin Python wrappers over the C ABI (include/missm_b200.h).
+
+Shape/dtype validation happens here, in Python; the CUDA entry points receive raw device
+pointers plus torch's current stream.  Nothing in this file computes on the CPU and nothing
+falls back to torch ops: if the library is missing, `_lib.lib()` raises.
+"""
 import ctypes
 
 import torch
 
-from . import _lib
-from ._lib import GemmArgs, check, lib, ptr, stream_ptr
+from ._lib import AttnArgs, GemmArgs, check, lib, stream_ptr
 
 EPI_LINEAR, EPI_GELU, EPI_RESID, EPI_DGELU, EPI_PATCH = range(5)
+BF16, F32 = torch.bfloat16, torch.float32
+
+
+def _p(t):
+    return ctypes.c_void_p(t.data_ptr()) if t is not None else None
 
 
 def _ld(t):
@@ -15,24 +23,25 @@ def _ld(t):
     return t.stride(0)
 
 
-def gemm(a, b, *, a_mn=False, b_mn=False, out=None, out_dtype=torch.bfloat16, bias=None,
+# --------------------------------------------------------------------------------------- GEMM
+def gemm(a, b, *, a_mn=False, b_mn=False, out=None, out_dtype=BF16, bias=None,
          epilogue=EPI_LINEAR, aux_in=None, aux_out=None, scale_cols=0, col_scale=1.0,
          patch_P=0, out_rows=None, split_k=0, force_bn=0):
     """C[m,n] = epilogue(sum_k A[m,k] B[n,k]).  `a`: [M,K] (or [K,M] if a_mn), `b`: [N,K]
     (or [K,N] if b_mn); both bf16 CUDA tensors, row-major."""
-    assert a.is_cuda and b.is_cuda and a.dtype == torch.bfloat16 and b.dtype == torch.bfloat16
+    assert a.is_cuda and b.is_cuda and a.dtype == BF16 and b.dtype == BF16
     M, K = (a.shape[1], a.shape[0]) if a_mn else (a.shape[0], a.shape[1])
     N, Kb = (b.shape[1], b.shape[0]) if b_mn else (b.shape[0], b.shape[1])
     assert K == Kb, f"contraction mismatch {K} vs {Kb}"
     if out is None:
         out = torch.empty((out_rows if out_rows is not None else M, N), device=a.device,
                           dtype=out_dtype)
-    assert out.dtype in (torch.bfloat16, torch.float32)
+    assert out.dtype in (BF16, F32)
     g = GemmArgs()
     g.A, g.B, g.C = a.data_ptr(), b.data_ptr(), out.data_ptr()
-    g.bias = bias.data_ptr() if bias is not None else None
     if bias is not None:
-        assert bias.dtype == torch.float32 and bias.numel() == N and bias.is_contiguous()
+        assert bias.dtype == F32 and bias.numel() == N and bias.is_contiguous()
+        g.bias = bias.data_ptr()
     g.aux_in = aux_in.data_ptr() if aux_in is not None else None
     g.aux_out = aux_out.data_ptr() if aux_out is not None else None
     g.M, g.N, g.K = M, N, K
@@ -41,8 +50,247 @@ def gemm(a, b, *, a_mn=False, b_mn=False, out=None, out_dtype=torch.bfloat16, bi
     g.ld_aux_out = _ld(aux_out) if aux_out is not None else 0
     g.a_mn, g.b_mn = int(a_mn), int(b_mn)
     g.epilogue = epilogue
-    g.out_f32 = int(out.dtype == torch.float32)
+    g.out_f32 = int(out.dtype == F32)
     g.scale_cols, g.col_scale = scale_cols, col_scale
     g.patch_P, g.split_k, g.force_bn = patch_P, split_k, force_bn
     check(lib().missm_gemm_bf16(ctypes.byref(g), stream_ptr()), "gemm_bf16")
     return out
+
+
+# ---------------------------------------------------------------------------------- attention
+class SeqLayout:
+    """Where sequence s / token t lives: row = (s // s_in)*seq_outer + (s % s_in)*seq_inner
+    + t*tok_stride."""
+
+    def __init__(self, n_seq, N, s_in=1, seq_outer=None, seq_inner=0, tok_stride=1):
+        self.n_seq, self.N, self.s_in = n_seq, N, s_in
+        self.seq_outer = N if seq_outer is None else seq_outer
+        self.seq_inner, self.tok_stride = seq_inner, tok_stride
+
+    @staticmethod
+    def spatial(n_seq, N):
+        return SeqLayout(n_seq, N)
+
+    @staticmethod
+    def temporal(B, T, N):
+        # activations are [(b t) n d]; sequence (b, n) runs over t
+        return SeqLayout(B * N, T, s_in=N, seq_outer=T * N, seq_inner=1, tok_stride=N)
+
+
+def _attn_args(qkv, out, lse, lay, H, causal, key_mask, mask_rows, mask_div):
+    D = qkv.shape[1] // 3
+    a = AttnArgs()
+    a.qkv, a.out, a.lse = qkv.data_ptr(), out.data_ptr(), lse.data_ptr()
+    a.ld_qkv, a.ld_o = _ld(qkv), _ld(out)
+    a.seq_outer, a.seq_inner, a.tok_stride = lay.seq_outer, lay.seq_inner, lay.tok_stride
+    a.D, a.H, a.N, a.head_dim = D, H, lay.N, D // H
+    a.n_seq, a.s_in = lay.n_seq, lay.s_in
+    a.causal, a.mask_div = int(causal), mask_div
+    if key_mask is not None:
+        assert key_mask.dtype == torch.int64 and key_mask.is_contiguous() and key_mask.shape[-1] == lay.N
+        a.key_mask = key_mask.data_ptr()
+    if mask_rows is not None:
+        assert mask_rows.dtype == torch.int32
+        a.mask_rows = mask_rows.data_ptr()
+    return a
+
+
+def attention_fwd(qkv, lay, H, *, causal=False, key_mask=None, mask_rows=None, mask_div=1):
+    """qkv bf16 [rows, 3D] (q pre-scaled) -> (out bf16 [rows, D], lse f32 [n_seq, H, N])."""
+    assert qkv.dtype == BF16 and qkv.is_cuda
+    D = qkv.shape[1] // 3
+    out = torch.empty((qkv.shape[0], D), device=qkv.device, dtype=BF16)
+    lse = torch.empty((lay.n_seq, H, lay.N), device=qkv.device, dtype=F32)
+    a = _attn_args(qkv, out, lse, lay, H, causal, key_mask, mask_rows, mask_div)
+    check(lib().missm_attention_fwd(ctypes.byref(a), stream_ptr()), "attention_fwd")
+    return out, lse
+
+
+def attention_bwd(qkv, out, lse, d_out, lay, H, q_scale, *, causal=False, key_mask=None,
+                  mask_rows=None, mask_div=1):
+    """-> dqkv bf16 [rows, 3D]; the q block is the gradient w.r.t. the UN-scaled projection."""
+    assert d_out.dtype == BF16 and d_out.shape == out.shape and _ld(d_out) == _ld(out)
+    dqkv = torch.empty_like(qkv)
+    delta = torch.empty_like(lse)
+    a = _attn_args(qkv, out, lse, lay, H, causal, key_mask, mask_rows, mask_div)
+    a.d_out, a.delta, a.dqkv, a.q_scale = d_out.data_ptr(), delta.data_ptr(), dqkv.data_ptr(), q_scale
+    check(lib().missm_attention_bwd(ctypes.byref(a), stream_ptr()), "attention_bwd")
+    return dqkv
+
+
+# ---------------------------------------------------------------------------------- layernorm
+def layernorm_fwd(x, gamma, beta, eps, *, out_dtype=BF16, row_index=None, n_rows=None,
+                  add_rows=None, add_period=0, add_div=0, want_stats=True):
+    """x f32 [R, D] -> (y [M, D], mean [M], rstd [M]); M = len(row_index) or R."""
+    assert x.dtype == F32 and x.is_cuda
+    D = x.shape[1]
+    M = n_rows if n_rows is not None else (row_index.numel() if row_index is not None else x.shape[0])
+    y = torch.empty((M, D), device=x.device, dtype=out_dtype)
+    mean = torch.empty((M,), device=x.device, dtype=F32) if want_stats else None
+    rstd = torch.empty((M,), device=x.device, dtype=F32) if want_stats else None
+    check(lib().missm_layernorm_fwd(_p(x), _ld(x), _p(row_index), _p(add_rows), add_period, add_div,
+                                    _p(x) if add_rows is not None else None, _p(gamma), _p(beta),
+                                    _p(y), _ld(y), int(out_dtype == BF16), _p(mean), _p(rstd), M, D,
+                                    eps, stream_ptr()), "layernorm_fwd")
+    return y, mean, rstd
+
+
+def layernorm_bwd(dy, x, mean, rstd, gamma, *, dres=None, row_index=None, dx=None,
+                  want_bf16=False, dx_bf16=None):
+    """-> (dx f32 like x, dx_bf16 or None, dgamma [D], dbeta [D]).  With row_index, dx must be a
+    pre-zeroed full-size tensor and only the indexed rows are written."""
+    D = x.shape[1]
+    M = dy.shape[0]
+    if dx is None:
+        assert row_index is None
+        dx = torch.empty_like(x)
+    if want_bf16 and dx_bf16 is None:
+        dx_bf16 = torch.empty(x.shape, device=x.device, dtype=BF16)
+    nparts = lib().missm_ln_bwd_num_partials(M)
+    partial = torch.empty((nparts, 2, D), device=x.device, dtype=F32)
+    dgamma = torch.empty((D,), device=x.device, dtype=F32)
+    dbeta = torch.empty((D,), device=x.device, dtype=F32)
+    check(lib().missm_layernorm_bwd(_p(dy), _ld(dy), int(dy.dtype == BF16), _p(x), _ld(x),
+                                    _p(row_index), _p(mean), _p(rstd), _p(gamma), _p(dres), _p(dx),
+                                    _p(dx_bf16), _p(partial), _p(dgamma), _p(dbeta), M, D,
+                                    stream_ptr()), "layernorm_bwd")
+    return dx, dx_bf16, dgamma, dbeta
+
+
+# ------------------------------------------------------------------------------------ helpers
+def cast_bf16(src, out=None, cols_dst=None):
+    """fp32 [rows, cols] -> bf16 [rows, cols_dst] (zero padded)."""
+    assert src.dtype == F32 and src.dim() == 2 and src.stride(1) == 1
+    rows, cols = src.shape
+    cols_dst = cols if cols_dst is None else cols_dst
+    if out is None:
+        out = torch.empty((rows, cols_dst), device=src.device, dtype=BF16)
+    check(lib().missm_cast_f32_bf16(_p(src), _ld(src), _p(out), _ld(out), rows, cols, cols_dst,
+                                    stream_ptr()), "cast_f32_bf16")
+    return out
+
+
+def colsum(x):
+    """bf16 [M, N] -> f32 [N] column sums (bias gradient)."""
+    assert x.dtype == BF16
+    M, N = x.shape
+    R = lib().missm_colsum_num_partials(M)
+    partial = torch.empty((R, N), device=x.device, dtype=F32)
+    out = torch.empty((N,), device=x.device, dtype=F32)
+    check(lib().missm_colsum_bf16(_p(x), _ld(x), M, N, _p(partial), _p(out), stream_ptr()), "colsum")
+    return out
+
+
+def patchify(pixels, ps, Kpad, sample_index=None, n_samples=None):
+    """pixels f32 [*, C, H, W] -> bf16 [Bn * gh * gw, Kpad] patches of the present samples."""
+    assert pixels.dtype == F32 and pixels.is_contiguous() and pixels.dim() == 4
+    _, C, H, W = pixels.shape
+    Bn = n_samples if n_samples is not None else pixels.shape[0]
+    out = torch.empty((Bn * (H // ps) * (W // ps), Kpad), device=pixels.device, dtype=BF16)
+    check(lib().missm_patchify(_p(pixels), _p(sample_index), _p(out), Bn, C, H, W, ps, Kpad,
+                               stream_ptr()), "patchify")
+    return out
+
+
+def cls_rows(cls, pos, tok, Bn, ntok):
+    check(lib().missm_cls_rows(_p(cls), _p(pos), _p(tok), Bn, ntok, tok.shape[1], stream_ptr()), "cls_rows")
+
+
+def embed_bwd(dtok, Bn, ntok):
+    D = dtok.shape[1]
+    dpos = torch.empty((ntok, D), device=dtok.device, dtype=F32)
+    dpatch = torch.empty((Bn * (ntok - 1), D), device=dtok.device, dtype=BF16)
+    check(lib().missm_embed_bwd(_p(dtok), _p(dpos), _p(dpatch), Bn, ntok, D, stream_ptr()), "embed_bwd")
+    return dpos, dpatch
+
+
+def frame_mean(x, Bn, T, out_dtype=BF16):
+    D = x.shape[1]
+    out = torch.empty((Bn, D), device=x.device, dtype=out_dtype)
+    check(lib().missm_frame_mean(_p(x), _p(out), int(out_dtype == BF16), Bn, T, D, stream_ptr()), "frame_mean")
+    return out
+
+
+def frame_mean_bwd(dout, Bn, T):
+    D = dout.shape[1]
+    din = torch.empty((Bn * T, D), device=dout.device, dtype=F32)
+    check(lib().missm_frame_mean_bwd(_p(dout), _p(din), Bn, T, D, stream_ptr()), "frame_mean_bwd")
+    return din
+
+
+def l2norm_scale_fwd(x, scale):
+    Bn, P = x.shape
+    y = torch.empty_like(x)
+    inv = torch.empty((Bn,), device=x.device, dtype=F32)
+    check(lib().missm_l2norm_scale_fwd(_p(x), _p(y), _p(inv), scale, Bn, P, stream_ptr()), "l2norm_fwd")
+    return y, inv
+
+
+def l2norm_scale_bwd(dy, x, inv, scale, out_dtype=BF16):
+    Bn, P = x.shape
+    dx = torch.empty((Bn, P), device=x.device, dtype=out_dtype)
+    check(lib().missm_l2norm_scale_bwd(_p(dy), _p(x), _p(inv), scale, _p(dx), int(out_dtype == BF16),
+                                       Bn, P, stream_ptr()), "l2norm_bwd")
+    return dx
+
+
+def text_embed_fwd(ids, tok_emb, pos_emb, sample_index=None, n_samples=None):
+    assert ids.dtype == torch.int64 and ids.is_contiguous()
+    L = ids.shape[1]
+    Bn = n_samples if n_samples is not None else ids.shape[0]
+    D = tok_emb.shape[1]
+    out = torch.empty((Bn * L, D), device=ids.device, dtype=F32)
+    check(lib().missm_text_embed_fwd(_p(ids), _p(sample_index), _p(tok_emb), _p(pos_emb), _p(out), Bn,
+                                     L, D, stream_ptr()), "text_embed_fwd")
+    return out
+
+
+def text_embed_bwd(ids, dx, vocab, sample_index=None, n_samples=None):
+    L = ids.shape[1]
+    Bn = n_samples if n_samples is not None else ids.shape[0]
+    D = dx.shape[1]
+    dtok = torch.zeros((vocab, D), device=dx.device, dtype=F32)
+    dpos = torch.empty((L, D), device=dx.device, dtype=F32)
+    check(lib().missm_text_embed_bwd(_p(ids), _p(sample_index), _p(dx), _p(dtok), _p(dpos), Bn, L, D,
+                                     stream_ptr()), "text_embed_bwd")
+    return dtok, dpos
+
+
+def argmax_rows(ids, sample_index=None, n_samples=None):
+    L = ids.shape[1]
+    Bn = n_samples if n_samples is not None else ids.shape[0]
+    out = torch.empty((Bn,), device=ids.device, dtype=torch.int32)
+    check(lib().missm_argmax_rows(_p(ids), _p(sample_index), _p(out), Bn, L, stream_ptr()), "argmax_rows")
+    return out
+
+
+# --------------------------------------------------------------------------------- compaction
+def compact_mask(missing_index, codes):
+    """missing_index int64 [B] (CUDA) -> (present_idx int32 [T, B], slot_of int32 [T, B],
+    counts int32 [T]) for the T towers whose missing codes are `codes`."""
+    assert missing_index.dtype == torch.int64 and missing_index.is_cuda and missing_index.is_contiguous()
+    B, T = missing_index.numel(), len(codes)
+    dev = missing_index.device
+    idx = torch.empty((T, B), device=dev, dtype=torch.int32)
+    slot = torch.empty((T, B), device=dev, dtype=torch.int32)
+    counts = torch.empty((T,), device=dev, dtype=torch.int32)
+    codes_host = (ctypes.c_int32 * T)(*[int(c) for c in codes])
+    check(lib().missm_compact_mask(_p(missing_index), B, ctypes.cast(codes_host, ctypes.c_void_p), T,
+                                   _p(idx), _p(slot), _p(counts), stream_ptr()), "compact_mask")
+    return idx, slot, counts
+
+
+def scatter_rows_zero(src, slot_of, B):
+    P = src.shape[1]
+    dst = torch.empty((B, P), device=slot_of.device, dtype=F32)
+    check(lib().missm_scatter_rows_zero(_p(src), _p(slot_of), _p(dst), B, P, stream_ptr()), "scatter_rows_zero")
+    return dst
+
+
+def gather_rows(src, idx, n_rows):
+    """dst[r] = src[idx[r]] for 2-D contiguous src (any dtype, row bytes multiple of 16)."""
+    assert src.is_contiguous()
+    row_bytes = src.stride(0) * src.element_size()
+    dst = torch.empty((n_rows,) + tuple(src.shape[1:]), device=src.device, dtype=src.dtype)
+    check(lib().missm_gather_rows(_p(src), _p(idx), _p(dst), n_rows, row_bytes, stream_ptr()), "gather_rows")
+    return dst

@@ -1,0 +1,273 @@
+"""Unit parity of every CUDA kernel against a plain fp32 torch statement of the same op
+(inputs rounded to bf16 where the kernel consumes bf16).  Run with `-m gpu` on a B200."""
+import math
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+
+
+def rel(a, b):
+    a, b = a.float(), b.float()
+    return ((a - b).norm() / b.norm().clamp_min(1e-30)).item()
+
+
+@pytest.fixture(scope="module")
+def ops():
+    from missm_b200 import ops as o
+    o.lib()
+    return o
+
+
+# ------------------------------------------------------------------------------------ GEMM
+@pytest.mark.parametrize("a_mn", [False, True])
+@pytest.mark.parametrize("b_mn", [False, True])
+@pytest.mark.parametrize("shape", [(128, 256, 64), (300, 520, 200), (1799, 3072, 1024), (64, 768, 1024)])
+def test_gemm_layouts(ops, a_mn, b_mn, shape):
+    M, N, K = shape
+    torch.manual_seed(M + N + K)
+    Mp = (M + 7) // 8 * 8 if a_mn else M
+    A = torch.randn(Mp, K, device=DEV).bfloat16()
+    B = torch.randn(N, K, device=DEV).bfloat16()
+    ref = A.float() @ B.float().t()
+    for bn in (128, 256):
+        out = ops.gemm(A.t().contiguous() if a_mn else A, B.t().contiguous() if b_mn else B,
+                       a_mn=a_mn, b_mn=b_mn, out_dtype=torch.float32, force_bn=bn, split_k=1)
+        assert rel(out, ref) < 1e-5
+
+
+def test_gemm_epilogues(ops):
+    torch.manual_seed(1)
+    M, N, K = 700, 1024, 512
+    A = torch.randn(M, K, device=DEV).bfloat16()
+    B = (torch.randn(N, K, device=DEV) * 0.05).bfloat16()
+    bias = torch.randn(N, device=DEV)
+    acc = A.float() @ B.float().t()
+    pre = acc + bias
+    out = ops.gemm(A, B, bias=bias, scale_cols=512, col_scale=0.125)
+    ref = pre.clone(); ref[:, :512] *= 0.125
+    assert rel(out, ref) < 4e-3
+    u = torch.empty(M, N, device=DEV, dtype=torch.bfloat16)
+    out = ops.gemm(A, B, bias=bias, epilogue=ops.EPI_GELU, aux_out=u)
+    assert rel(u, pre) < 4e-3 and rel(out, pre * torch.sigmoid(1.702 * pre)) < 4e-3
+    res = torch.randn(M, N, device=DEV)
+    out = ops.gemm(A, B, bias=bias, epilogue=ops.EPI_RESID, aux_in=res, out_dtype=torch.float32)
+    assert rel(out, res + pre) < 1e-5
+    res2 = res.clone()
+    ops.gemm(A, B, bias=bias, epilogue=ops.EPI_RESID, aux_in=res2, out=res2)
+    assert rel(res2, res + pre) < 1e-5
+    uu = torch.randn(M, N, device=DEV).bfloat16()
+    out = ops.gemm(A, B, epilogue=ops.EPI_DGELU, aux_in=uu)
+    s = torch.sigmoid(1.702 * uu.float())
+    assert rel(out, acc * (s * (1 + 1.702 * uu.float() * (1 - s)))) < 4e-3
+    P, Bsz = 100, 7
+    pos = torch.randn(P + 1, N, device=DEV)
+    tok = torch.zeros(Bsz * (P + 1), N, device=DEV)
+    ops.gemm(A, B, epilogue=ops.EPI_PATCH, aux_in=pos, out=tok, patch_P=P)
+    ref = torch.zeros(Bsz, P + 1, N, device=DEV); ref[:, 1:] = acc.view(Bsz, P, N) + pos[1:]
+    assert rel(tok, ref.view(-1, N)) < 1e-5
+
+
+def test_gemm_splitk_wgrad(ops):
+    torch.manual_seed(2)
+    Mtok = 257 * 9
+    dY = torch.randn(Mtok, 1024, device=DEV).bfloat16()
+    X = torch.randn(Mtok, 1024, device=DEV).bfloat16()
+    out = ops.gemm(dY, X, a_mn=True, b_mn=True, out_dtype=torch.float32)
+    assert rel(out, dY.float().t() @ X.float()) < 1e-5
+    # K tail (592-wide patch rows) and M == 0
+    Xp = torch.randn(Mtok, 592, device=DEV).bfloat16()
+    out = ops.gemm(dY, Xp, a_mn=True, b_mn=True, out_dtype=torch.float32)
+    assert rel(out, dY.float().t() @ Xp.float()) < 1e-5
+    e = ops.gemm(torch.empty(0, 64, device=DEV, dtype=torch.bfloat16), X[:8, :64].contiguous())
+    assert e.shape == (0, 8)
+
+
+# ------------------------------------------------------------------------------- layernorm
+@pytest.mark.parametrize("D", [256, 768, 1024])
+def test_layernorm_fwd_bwd(ops, D):
+    torch.manual_seed(D)
+    M = 1000
+    x = (torch.randn(M, D, device=DEV) * 3 + 0.5).requires_grad_(True)
+    g = torch.randn(D, device=DEV).requires_grad_(True)
+    b = torch.randn(D, device=DEV).requires_grad_(True)
+    ref = torch.nn.functional.layer_norm(x, (D,), g, b, 1e-5)
+    y, mean, rstd = ops.layernorm_fwd(x.detach(), g.detach(), b.detach(), 1e-5, out_dtype=torch.float32)
+    assert rel(y, ref) < 1e-6
+    yb, _, _ = ops.layernorm_fwd(x.detach(), g.detach(), b.detach(), 1e-5)
+    assert rel(yb, ref) < 4e-3
+    dy = torch.randn(M, D, device=DEV)
+    dres = torch.randn(M, D, device=DEV)
+    ref.backward(dy)
+    dx, dxb, dg, db = ops.layernorm_bwd(dy, x.detach(), mean, rstd, g.detach(), dres=dres, want_bf16=True)
+    assert rel(dx, x.grad + dres) < 1e-5
+    assert rel(dxb, x.grad + dres) < 4e-3
+    assert rel(dg, g.grad) < 1e-5 and rel(db, b.grad) < 1e-5
+    # bf16 dy
+    dx2, _, dg2, _ = ops.layernorm_bwd(dy.bfloat16(), x.detach(), mean, rstd, g.detach())
+    x.grad = None; g.grad = None
+    torch.nn.functional.layer_norm(x, (D,), g, b, 1e-5).backward(dy.bfloat16().float())
+    assert rel(dx2, x.grad) < 1e-5 and rel(dg2, g.grad) < 1e-5
+
+
+def test_layernorm_gather_and_add(ops):
+    torch.manual_seed(3)
+    D, N, B, T = 256, 5, 6, 3
+    x = torch.randn(B * T * N, D, device=DEV)
+    g, b = torch.randn(D, device=DEV), torch.randn(D, device=DEV)
+    rows = (torch.arange(B * T, device=DEV, dtype=torch.int32) * N)
+    y, mean, rstd = ops.layernorm_fwd(x, g, b, 1e-5, out_dtype=torch.float32, row_index=rows)
+    ref = torch.nn.functional.layer_norm(x[rows.long()], (D,), g, b, 1e-5)
+    assert rel(y, ref) < 1e-6
+    dy = torch.randn(B * T, D, device=DEV)
+    dx = torch.zeros_like(x)
+    ops.layernorm_bwd(dy, x, mean, rstd, g, row_index=rows, dx=dx)
+    xr = x.clone().requires_grad_(True)
+    torch.nn.functional.layer_norm(xr[rows.long()], (D,), g, b, 1e-5).backward(dy)
+    assert rel(dx, xr.grad) < 1e-5
+    # temporal embedding add: x <- x + temb[(row // N) % T]
+    temb = torch.randn(T, D, device=DEV)
+    x2 = x.clone()
+    y2, _, _ = ops.layernorm_fwd(x2, g, b, 1e-5, out_dtype=torch.float32, add_rows=temb, add_period=T, add_div=N)
+    xe = (x.view(B, T, N, D) + temb[None, :, None, :]).reshape(-1, D)
+    assert rel(x2, xe) < 1e-6
+    assert rel(y2, torch.nn.functional.layer_norm(xe, (D,), g, b, 1e-5)) < 1e-6
+
+
+# ------------------------------------------------------------------------------- attention
+def _attn_ref(q, k, v, causal, kmask):
+    # q,k,v: [S, H, N, hd] fp32; q already scaled
+    s = q @ k.transpose(-1, -2)
+    N = q.shape[2]
+    if causal:
+        s = s + torch.full((N, N), float("-inf"), device=q.device).triu(1)
+    if kmask is not None:
+        s = s.masked_fill(kmask[:, None, None, :] == 0, float("-inf"))
+    return torch.softmax(s, -1) @ v
+
+
+@pytest.mark.parametrize("cfg", [(3, 16, 257, False, False), (2, 12, 77, True, True), (2, 16, 593, False, False),
+                                 (5, 4, 8, False, False), (1, 2, 64, True, False), (2, 2, 130, False, True)])
+def test_attention_fwd_bwd(ops, cfg):
+    S, H, N, causal, use_mask = cfg
+    torch.manual_seed(N)
+    D = H * 64
+    qkv = (torch.randn(S * N, 3 * D, device=DEV) * 0.7).bfloat16()
+    kmask = None
+    if use_mask:
+        lens = torch.randint(1, N + 1, (S,), device=DEV)
+        kmask = (torch.arange(N, device=DEV)[None, :] < lens[:, None]).long().contiguous()
+    lay = ops.SeqLayout.spatial(S, N)
+    out, lse = ops.attention_fwd(qkv, lay, H, causal=causal, key_mask=kmask)
+    f = qkv.float().view(S, N, 3, H, 64).permute(2, 0, 3, 1, 4).contiguous().requires_grad_(True)
+    ref = _attn_ref(f[0], f[1], f[2], causal, kmask)          # [S,H,N,hd]
+    ref_o = ref.permute(0, 2, 1, 3).reshape(S * N, D)
+    assert rel(out, ref_o) < 6e-3
+    d_out = (torch.randn(S * N, D, device=DEV)).bfloat16()
+    ref_o.backward(d_out.float())
+    q_scale = 0.125
+    dqkv = ops.attention_bwd(qkv, out, lse, d_out, lay, H, q_scale, causal=causal, key_mask=kmask)
+    gref = f.grad.permute(1, 3, 0, 2, 4).reshape(S * N, 3 * D).clone()
+    gref[:, :D] *= q_scale
+    assert rel(dqkv[:, :D], gref[:, :D]) < 1.5e-2
+    assert rel(dqkv[:, D:2 * D], gref[:, D:2 * D]) < 1.5e-2
+    assert rel(dqkv[:, 2 * D:], gref[:, 2 * D:]) < 1.5e-2
+
+
+def test_attention_temporal_layout(ops):
+    """Temporal attention reads [(b t) n d] in place: sequence (b, n) over t."""
+    torch.manual_seed(5)
+    B, T, N, H = 2, 8, 5, 2
+    D = H * 64
+    qkv = (torch.randn(B * T * N, 3 * D, device=DEV) * 0.7).bfloat16()
+    lay = ops.SeqLayout.temporal(B, T, N)
+    out, lse = ops.attention_fwd(qkv, lay, H)
+    f = qkv.float().view(B, T, N, 3, H, 64).permute(3, 0, 2, 4, 1, 5).reshape(3, B * N, H, T, 64)
+    ref = _attn_ref(f[0], f[1], f[2], False, None)           # [(b n), H, T, hd]
+    ref_o = ref.view(B, N, H, T, 64).permute(0, 3, 1, 2, 4).reshape(B * T * N, D)
+    assert rel(out, ref_o) < 6e-3
+
+
+# --------------------------------------------------------------------------------- helpers
+def test_cast_colsum_patchify(ops):
+    torch.manual_seed(6)
+    w = torch.randn(300, 588, device=DEV)
+    wb = ops.cast_bf16(w, cols_dst=592)
+    assert torch.equal(wb[:, :588], w.bfloat16()) and (wb[:, 588:] == 0).all()
+    x = torch.randn(3000, 1024, device=DEV).bfloat16()
+    assert rel(ops.colsum(x), x.float().sum(0)) < 1e-5
+    px = torch.randn(5, 3, 28, 70, device=DEV)
+    idx = torch.tensor([4, 0, 2], device=DEV, dtype=torch.int32)
+    pt = ops.patchify(px, 14, 592, sample_index=idx, n_samples=3)
+    ref = torch.nn.functional.unfold(px[idx.long()], kernel_size=14, stride=14).transpose(1, 2).reshape(-1, 588)
+    assert torch.equal(pt[:, :588], ref.bfloat16()) and (pt[:, 588:] == 0).all()
+
+
+def test_embed_pool_l2norm(ops):
+    torch.manual_seed(7)
+    B, ntok, D = 4, 9, 256
+    dtok = torch.randn(B * ntok, D, device=DEV)
+    dpos, dpatch = ops.embed_bwd(dtok, B, ntok)
+    assert rel(dpos, dtok.view(B, ntok, D).sum(0)) < 1e-6
+    assert torch.equal(dpatch, dtok.view(B, ntok, D)[:, 1:].reshape(-1, D).bfloat16())
+    x = torch.randn(B * 3, D, device=DEV)
+    assert rel(ops.frame_mean(x, B, 3, torch.float32), x.view(B, 3, D).mean(1)) < 1e-6
+    d = torch.randn(B, D, device=DEV)
+    assert rel(ops.frame_mean_bwd(d, B, 3), (d[:, None, :] / 3).expand(B, 3, D).reshape(-1, D)) < 1e-6
+    xr = torch.randn(B, 768, device=DEV, requires_grad=True)
+    scale = math.exp(2.6592)
+    ref = xr / xr.norm(p=2, dim=-1, keepdim=True) * scale
+    y, inv = ops.l2norm_scale_fwd(xr.detach(), scale)
+    assert rel(y, ref) < 1e-6
+    dy = torch.randn(B, 768, device=DEV)
+    ref.backward(dy)
+    assert rel(ops.l2norm_scale_bwd(dy, xr.detach(), inv, scale, torch.float32), xr.grad) < 1e-5
+
+
+def test_text_embed_argmax(ops):
+    torch.manual_seed(8)
+    B, L, D, V = 5, 77, 256, 1000
+    ids = torch.randint(1, V - 2, (B, L), device=DEV)
+    ids[:, 0] = V - 2
+    for b in range(B):
+        ids[b, 5 + b:] = V - 1          # EOT + EOT padding -> first maximum wins
+    tok, pos = torch.randn(V, D, device=DEV), torch.randn(L, D, device=DEV)
+    sel = torch.tensor([3, 1, 4], device=DEV, dtype=torch.int32)
+    out = ops.text_embed_fwd(ids, tok, pos, sample_index=sel, n_samples=3)
+    ref = tok[ids[sel.long()]] + pos[None]
+    assert torch.equal(out, ref.view(-1, D))
+    rows = ops.argmax_rows(ids, sample_index=sel, n_samples=3)
+    exp = torch.arange(3, device=DEV) * L + ids[sel.long()].to(torch.int32).argmax(-1)
+    assert torch.equal(rows.long(), exp)
+    dx = torch.randn(3 * L, D, device=DEV)
+    dtok, dpos = ops.text_embed_bwd(ids, dx, V, sample_index=sel, n_samples=3)
+    rt = torch.zeros(V, D, device=DEV).index_add_(0, ids[sel.long()].view(-1), dx)
+    assert rel(dtok, rt) < 1e-5 and rel(dpos, dx.view(3, L, D).sum(0)) < 1e-6
+
+
+# ------------------------------------------------------------------------------ compaction
+@pytest.mark.parametrize("B", [1, 8, 64, 333])
+def test_compaction_bit_exact(ops, B):
+    """Indices must equal torch.nonzero(missing_index != code) exactly."""
+    g = torch.Generator().manual_seed(B)
+    mi = torch.randint(0, 7, (B,), generator=g).to(DEV)
+    codes = [1, 2, 3, 4, 5, 6]
+    idx, slot, counts = ops.compact_mask(mi, codes)
+    c = counts.cpu()
+    for t, code in enumerate(codes):
+        exp = torch.nonzero(mi != code).flatten().to(torch.int32)
+        assert int(c[t]) == exp.numel()
+        assert torch.equal(idx[t, :exp.numel()], exp)
+        s = torch.full((B,), -1, dtype=torch.int32, device=DEV)
+        s[exp.long()] = torch.arange(exp.numel(), dtype=torch.int32, device=DEV)
+        assert torch.equal(slot[t], s)
+    # gather / zero-filled scatter round trip
+    x = torch.randn(B, 768, device=DEV)
+    n = int(c[3])
+    gath = ops.gather_rows(x, idx[3], n)
+    assert torch.equal(gath, x[idx[3, :n].long()])
+    back = ops.scatter_rows_zero(gath, slot[3], B)
+    ref = x.clone(); ref[mi == codes[3]] = 0
+    assert torch.equal(back, ref)
