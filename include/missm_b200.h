@@ -133,10 +133,15 @@ int missm_colsum_num_partials(int32_t M);
 int missm_colsum_bf16(const void* x, int64_t ldx, int32_t M, int32_t N, float* partial, float* out,
                       void* stream);
 /* Conv2d(k = stride = ps, no bias) input patches (video/modeling_video.py:29-35,45):
- * pixels f32 [*, C, H, W] (sample b read from sample_index ? sample_index[b] : b)
- * -> bf16 [Bn * (H/ps) * (W/ps), Kpad], column (c*ps + i)*ps + j, zero padded */
+ * pixels f32 [*, C, T, H, W] (T = 1 for images; the video reshape `b c t h w -> (b t) c h w` of
+ * modeling_image.py:636-639 is folded in; sample b read from sample_index ? sample_index[b] : b)
+ * -> bf16 [Bn * T * (H/ps) * (W/ps), Kpad], column (c*ps + i)*ps + j, zero padded */
 int missm_patchify(const float* pixels, const int32_t* sample_index, void* patches, int32_t Bn,
-                   int32_t C, int32_t H, int32_t W, int32_t ps, int32_t Kpad, void* stream);
+                   int32_t C, int32_t T, int32_t H, int32_t W, int32_t ps, int32_t Kpad, void* stream);
+/* out[g] = sum of rows r of x f32 [M, D] with (r / div) % period == g  (temporal-embedding grad) */
+int missm_colsum_grouped_f32(const float* x, int32_t M, int32_t D, int32_t period, int32_t div,
+                             float* out, void* stream);
+int missm_copy_f32(const float* src, float* dst, int64_t n, void* stream);
 /* tok[b, 0, :] = class_embedding + position_embedding[0]   (modeling_video.py:48-50) */
 int missm_cls_rows(const float* cls, const float* pos, float* tok, int32_t Bn, int32_t ntok, int32_t D,
                    void* stream);
@@ -177,6 +182,35 @@ int missm_scatter_rows_zero(const float* src, const int32_t* slot_of, float* dst
 /* dst[r] = src[idx[r]]   (rows of row_bytes bytes, multiple of 16) */
 int missm_gather_rows(const void* src, const int32_t* idx, void* dst, int32_t n_rows,
                       int64_t row_bytes, void* stream);
+
+/* ---------------------------------------------------------------------------------------
+ * Masked fusion of the default `sum` head, fp32 (modal_sum.forward, src/model/baseline.py:52-61):
+ *   pre[b] = sum_m (missing_index[b] != codes[m]) * (emb_m[b] W_m^T + bias_m);  out = LayerNorm(pre)
+ * emb_m f32 [B, P], weight_m f32 [Fd, P], bias_m f32 [Fd]; pre/out f32 [B, Fd]; mean/rstd f32 [B].
+ * bwd: d_emb_m [B, P], d_weight_m [Fd, P], d_bias_m [Fd], d_gamma/d_beta [Fd];
+ *      workspace = 3 * B * Fd floats.
+ * ------------------------------------------------------------------------------------- */
+typedef struct missm_fusion_sum_args {
+  const float* emb[MISSM_MAX_TOWERS];
+  const float* weight[MISSM_MAX_TOWERS];
+  const float* bias[MISSM_MAX_TOWERS];
+  float* d_emb[MISSM_MAX_TOWERS];
+  float* d_weight[MISSM_MAX_TOWERS];
+  float* d_bias[MISSM_MAX_TOWERS];
+  int32_t codes[MISSM_MAX_TOWERS];
+  const int64_t* missing_index;
+  const float* gamma;
+  const float* beta;
+  float* pre;
+  float* out;
+  float* mean;
+  float* rstd;
+  int32_t n_modal, B, P, Fd;
+  float eps;
+} missm_fusion_sum_args;
+int missm_fusion_sum_fwd(const missm_fusion_sum_args* args, void* stream);
+int missm_fusion_sum_bwd(const missm_fusion_sum_args* args, const float* d_out, float* workspace,
+                         float* d_gamma, float* d_beta, void* stream);
 
 #ifdef __cplusplus
 }

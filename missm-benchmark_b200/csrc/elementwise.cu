@@ -81,23 +81,25 @@ __global__ void reduce_rows_kernel(const float* __restrict__ partial, int R, int
 // patches bf16 [B * gh * gw, Kpad], column k = (c * ps + i) * ps + j  (Conv2d weight order)
 // ---------------------------------------------------------------------------------------
 __global__ void patchify_kernel(const float* __restrict__ px, const int* __restrict__ sample_index,
-                                __nv_bfloat16* __restrict__ out, int Bn, int C, int H, int W,
+                                __nv_bfloat16* __restrict__ out, int Bn, int C, int T, int H, int W,
                                 int ps, int gh, int gw, int Kpad) {
   // one warp per (sample, channel, pixel row): reads W contiguous floats (coalesced)
   const int lane = threadIdx.x & 31;
   const long warp_global = (blockIdx.x * static_cast<long>(blockDim.x) + threadIdx.x) >> 5;
   const long nwarps = (static_cast<long>(gridDim.x) * blockDim.x) >> 5;
-  const long total = static_cast<long>(Bn) * C * gh * ps;  // rows that belong to some patch
-  for (long t = warp_global; t < total; t += nwarps) {
-    const int i = static_cast<int>(t % ps);
-    const int py = static_cast<int>((t / ps) % gh);
-    const int c = static_cast<int>((t / (static_cast<long>(ps) * gh)) % C);
-    const int b = static_cast<int>(t / (static_cast<long>(ps) * gh * C));
+  // input is [B, C, T, H, W] (T = 1: plain images); output image index = b * T + t
+  const long total = static_cast<long>(Bn) * T * C * gh * ps;  // pixel rows that belong to some patch
+  for (long w = warp_global; w < total; w += nwarps) {
+    const int i = static_cast<int>(w % ps);
+    const int py = static_cast<int>((w / ps) % gh);
+    const int c = static_cast<int>((w / (static_cast<long>(ps) * gh)) % C);
+    const int t = static_cast<int>((w / (static_cast<long>(ps) * gh * C)) % T);
+    const int b = static_cast<int>(w / (static_cast<long>(ps) * gh * C * T));
     const long src_b = sample_index ? sample_index[b] : b;
-    const float* row = px + ((src_b * C + c) * H + (py * ps + i)) * W;
+    const float* row = px + (((src_b * C + c) * T + t) * H + (py * ps + i)) * W;
     for (int xcol = lane; xcol < gw * ps; xcol += 32) {
       const int pxi = xcol / ps, j = xcol % ps;
-      const long prow = (static_cast<long>(b) * gh + py) * gw + pxi;
+      const long prow = ((static_cast<long>(b) * T + t) * gh + py) * gw + pxi;
       out[prow * Kpad + (c * ps + i) * ps + j] = __float2bfloat16(row[xcol]);
     }
   }
@@ -269,6 +271,20 @@ __global__ void argmax_rows_kernel(const int64_t* __restrict__ ids, const int* _
   out_rows[b] = b * L + best;  // row in the compacted [Bn*L, D] token matrix
 }
 
+// out[g, :] = sum over rows r with (r / div) % period == g of x[r, :]   (x f32 [M, D])
+// (gradient of the temporal embedding, modeling_image.py:113)
+__global__ void colsum_grouped_kernel(const float* __restrict__ x, int M, int D, int period, int div,
+                                      float* __restrict__ out) {
+  const int g = blockIdx.y;
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= D) return;
+  float s = 0.f;
+  const int span = period * div;
+  for (int r0 = g * div; r0 < M; r0 += span)
+    for (int r = r0; r < min(r0 + div, M); ++r) s += x[static_cast<long>(r) * D + c];
+  out[static_cast<long>(g) * D + c] = s;
+}
+
 static inline int grid_for(long total, int threads) {
   long b = (total + threads - 1) / threads;
   long cap = 16L * kNumSMs;
@@ -316,18 +332,18 @@ extern "C" int missm_colsum_bf16(const void* x, int64_t ldx, int32_t M, int32_t 
 }
 
 extern "C" int missm_patchify(const float* pixels, const int32_t* sample_index, void* patches,
-                              int32_t Bn, int32_t C, int32_t H, int32_t W, int32_t ps, int32_t Kpad,
-                              void* stream) {
+                              int32_t Bn, int32_t C, int32_t T, int32_t H, int32_t W, int32_t ps,
+                              int32_t Kpad, void* stream) {
   if (Bn == 0) return 0;
   const int gh = H / ps, gw = W / ps, K = C * ps * ps;
-  MISSM_REQUIRE(Kpad >= K && Kpad % 8 == 0, "patchify: Kpad=%d K=%d", Kpad, K);
-  const long rows = static_cast<long>(Bn) * gh * gw;
+  MISSM_REQUIRE(Kpad >= K && Kpad % 8 == 0 && T >= 1, "patchify: Kpad=%d K=%d T=%d", Kpad, K, T);
+  const long rows = static_cast<long>(Bn) * T * gh * gw;
   if (Kpad > K)
     zero_pad_cols_kernel<<<grid_for(rows * (Kpad - K), 256), 256, 0, ST(stream)>>>(
         static_cast<__nv_bfloat16*>(patches), rows, K, Kpad);
-  const long warps = static_cast<long>(Bn) * C * gh * ps;
+  const long warps = static_cast<long>(Bn) * T * C * gh * ps;
   patchify_kernel<<<grid_for(warps * 32, 256), 256, 0, ST(stream)>>>(
-      pixels, sample_index, static_cast<__nv_bfloat16*>(patches), Bn, C, H, W, ps, gh, gw, Kpad);
+      pixels, sample_index, static_cast<__nv_bfloat16*>(patches), Bn, C, T, H, W, ps, gh, gw, Kpad);
   MISSM_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
@@ -404,5 +420,20 @@ extern "C" int missm_argmax_rows(const int64_t* ids, const int32_t* sample_index
   if (Bn == 0) return 0;
   argmax_rows_kernel<<<(Bn + 127) / 128, 128, 0, ST(stream)>>>(ids, sample_index, out_rows, Bn, L);
   MISSM_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int missm_colsum_grouped_f32(const float* x, int32_t M, int32_t D, int32_t period, int32_t div,
+                                        float* out, void* stream) {
+  MISSM_REQUIRE(period > 0 && div > 0, "colsum_grouped: period=%d div=%d", period, div);
+  dim3 grid((D + 127) / 128, period);
+  colsum_grouped_kernel<<<grid, 128, 0, ST(stream)>>>(x, M, D, period, div, out);
+  MISSM_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int missm_copy_f32(const float* src, float* dst, int64_t n, void* stream) {
+  if (n == 0) return 0;
+  MISSM_CHECK_CUDA(cudaMemcpyAsync(dst, src, sizeof(float) * n, cudaMemcpyDeviceToDevice, ST(stream)));
   return 0;
 }

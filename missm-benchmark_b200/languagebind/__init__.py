@@ -1,0 +1,14 @@
+"""Drop-in `languagebind` package: the names train_ddp.py:12 / test.py:12 import
+(`LanguageBind, to_device, transform_dict, LanguageBindImageTokenizer`) plus `model_dict` /
+`config_dict`, backed by the B200 CUDA path (missm_b200).  Put the directory that contains this
+package first on PYTHONPATH and the reference scripts run unchanged."""
+from missm_b200.bank import LanguageBind, to_device, model_dict, config_dict, MISSING_TYPE_INDEX  # noqa: F401
+from missm_b200.config import (LanguageBindImageConfig, LanguageBindVideoConfig, LanguageBindDepthConfig,  # noqa: F401
+                               LanguageBindAudioConfig, LanguageBindThermalConfig)
+from missm_b200.towers import (LanguageBindImage, LanguageBindVideo, LanguageBindDepth,  # noqa: F401
+                               LanguageBindAudio, LanguageBindThermal)
+from missm_b200.io_boundary import (transform_dict, LanguageBindImageTokenizer, LanguageBindVideoTokenizer,  # noqa: F401
+                                    LanguageBindDepthTokenizer, LanguageBindAudioTokenizer,
+                                    LanguageBindThermalTokenizer, LanguageBindImageProcessor,
+                                    LanguageBindVideoProcessor, LanguageBindDepthProcessor,
+                                    LanguageBindAudioProcessor, LanguageBindThermalProcessor)

@@ -19,7 +19,9 @@ SIGNATURES = {
     "missm_cast_f32_bf16": [P, L, P, L, I, I, I, P],
     "missm_colsum_num_partials": [I],
     "missm_colsum_bf16": [P, L, I, I, P, P, P],
-    "missm_patchify": [P, P, P, I, I, I, I, I, I, P],
+    "missm_patchify": [P, P, P, I, I, I, I, I, I, I, P],
+    "missm_colsum_grouped_f32": [P, I, I, I, I, P, P],
+    "missm_copy_f32": [P, P, L, P],
     "missm_cls_rows": [P, P, P, I, I, I, P],
     "missm_embed_bwd": [P, P, P, I, I, I, P],
     "missm_frame_mean": [P, P, I, I, I, I, P],
@@ -32,6 +34,8 @@ SIGNATURES = {
     "missm_compact_mask": [P, I, P, I, P, P, P, P],
     "missm_scatter_rows_zero": [P, P, P, I, I, P],
     "missm_gather_rows": [P, P, P, I, L, P],
+    "missm_fusion_sum_fwd": [P, P],
+    "missm_fusion_sum_bwd": [P, P, P, P, P, P],
 }
 # exported but with non-standard return types / no args
 OTHER_EXPORTS = ["missm_version", "missm_last_error"]

@@ -1,0 +1,289 @@
+"""torch.autograd.Functions that drive the CUDA kernels (one Function per residual block so
+that DDP's bucket hooks see parameter gradients layer by layer, last layer first).
+
+Activations: fp32 residual stream [M, D]; bf16 GEMM operands; fp32 accumulation everywhere.
+Every Function returns an explicit gradient (never None) for every parameter it receives --
+DDP at train_ddp.py:189 runs with find_unused_parameters=False.
+"""
+import torch
+
+from . import ops
+from .ops import BF16, F32, EPI_DGELU, EPI_GELU, EPI_PATCH, EPI_RESID
+
+# ------------------------------------------------------------------------------------------
+# side channel: bf16 copy of a residual-stream gradient, produced by the LayerNorm-backward of
+# block k and consumed by block k-1 (autograd itself only carries the fp32 tensor)
+# ------------------------------------------------------------------------------------------
+_GRAD_BF16 = {}
+
+
+def _publish_bf16(grad_f32, grad_bf16):
+    # holding grad_f32 keeps its storage alive, so a pointer match means "the same tensor"
+    _GRAD_BF16[grad_f32.data_ptr()] = (grad_f32, grad_bf16)
+
+
+def _bf16_of(grad_f32):
+    hit = _GRAD_BF16.pop(grad_f32.data_ptr(), None)
+    if hit is not None and hit[0].shape == grad_f32.shape and hit[0]._version == grad_f32._version:
+        return hit[1]
+    return ops.cast_bf16(grad_f32)
+
+
+def reset_side_channel():
+    _GRAD_BF16.clear()
+
+
+def _contig(g):
+    return g if g.is_contiguous() else g.contiguous()
+
+
+# ------------------------------------------------------------------------------------------
+# bf16 operand copies of fp32 master weights, cached on the owning module by parameter version
+# ------------------------------------------------------------------------------------------
+def cached_weight(cache, name, params, build):
+    ver = tuple((p._version, p.data_ptr()) for p in params)
+    hit = cache.get(name)
+    if hit is not None and hit[0] == ver:
+        return hit[1]
+    val = build()
+    cache[name] = (ver, val)
+    return val
+
+
+def _w2d(p):
+    return p.detach().reshape(p.shape[0], -1)
+
+
+def bf16_weight(cache, name, p, cols_dst=None):
+    return cached_weight(cache, name, (p,), lambda: ops.cast_bf16(_w2d(p), cols_dst=cols_dst))
+
+
+def packed_qkv(cache, qw, kw, vw, qb, kb, vb):
+    def build():
+        D = qw.shape[0]
+        w = torch.empty((3 * D, qw.shape[1]), device=qw.device, dtype=BF16)
+        b = torch.empty((3 * D,), device=qw.device, dtype=F32)
+        for i, (wi, bi) in enumerate(((qw, qb), (kw, kb), (vw, vb))):
+            ops.cast_bf16(wi.detach(), out=w[i * D:(i + 1) * D])
+            ops.copy_f32(bi.detach(), b[i * D:(i + 1) * D])
+        return w, b
+    return cached_weight(cache, "qkv", (qw, kw, vw, qb, kb, vb), build)
+
+
+class AttnMeta:
+    """Static description of one attention block."""
+
+    def __init__(self, H, eps, layout, causal=False, key_mask=None, mask_rows=None, mask_div=1,
+                 add_period=0, add_div=0):
+        self.H, self.eps, self.layout = H, eps, layout
+        self.causal, self.key_mask, self.mask_rows, self.mask_div = causal, key_mask, mask_rows, mask_div
+        self.add_period, self.add_div = add_period, add_div
+
+
+# ------------------------------------------------------------------------------------------
+# x + OutProj(Attention(QKV(LN(x [+ temporal embedding]))))
+#   reference: CLIPEncoderLayer.forward, languagebind/image/modeling_image.py:105-127 (temporal)
+#   and :137-146 (spatial); CLIPAttention = transformers 4.3x
+# ------------------------------------------------------------------------------------------
+class AttnBlockFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, meta, cache, ln_w, ln_b, qw, qb, kw, kb, vw, vb, ow, ob, temb):
+        D = x.shape[1]
+        hd = D // meta.H
+        wqkv, bqkv = packed_qkv(cache, qw, kw, vw, qb, kb, vb)
+        wo = bf16_weight(cache, "o", ow)
+        if temb is not None:
+            # hidden_states + temporal_embedding[:, :t]  (modeling_image.py:110-114); out of place
+            x_res = torch.empty_like(x)
+            h, mean, rstd = ops.layernorm_fwd(x, ln_w, ln_b, meta.eps, add_rows=temb.detach().reshape(-1, D),
+                                              add_period=meta.add_period, add_div=meta.add_div, x_out=x_res)
+        else:
+            x_res = x
+            h, mean, rstd = ops.layernorm_fwd(x, ln_w, ln_b, meta.eps)
+        qkv = ops.gemm(h, wqkv, bias=bqkv, scale_cols=D, col_scale=hd ** -0.5)
+        attn, lse = ops.attention_fwd(qkv, meta.layout, meta.H, causal=meta.causal, key_mask=meta.key_mask,
+                                      mask_rows=meta.mask_rows, mask_div=meta.mask_div)
+        out = ops.gemm(attn, wo, bias=ob.detach(), epilogue=EPI_RESID, aux_in=x_res, out_dtype=F32)
+        ctx.meta = meta
+        ctx.has_temb = temb is not None
+        ctx.save_for_backward(x_res, mean, rstd, h, qkv, attn, lse, wqkv, wo, ln_w)
+        return out
+
+    @staticmethod
+    def backward(ctx, d_out):
+        x_res, mean, rstd, h, qkv, attn, lse, wqkv, wo, ln_w = ctx.saved_tensors
+        meta = ctx.meta
+        D = x_res.shape[1]
+        hd = D // meta.H
+        d_out = _contig(d_out)
+        d_out_b = _bf16_of(d_out)
+        d_ow = ops.gemm(d_out_b, attn, a_mn=True, b_mn=True, out_dtype=F32)          # dY^T @ attn
+        d_ob = ops.colsum(d_out_b)
+        d_attn = ops.gemm(d_out_b, wo, b_mn=True)                                      # dY @ Wo
+        dqkv = ops.attention_bwd(qkv, attn, lse, d_attn, meta.layout, meta.H, hd ** -0.5, causal=meta.causal,
+                                 key_mask=meta.key_mask, mask_rows=meta.mask_rows, mask_div=meta.mask_div)
+        d_wqkv = ops.gemm(dqkv, h, a_mn=True, b_mn=True, out_dtype=F32)               # [3D, D]
+        d_bqkv = ops.colsum(dqkv)
+        d_h = ops.gemm(dqkv, wqkv, b_mn=True)
+        dx, dx_b, d_lnw, d_lnb = ops.layernorm_bwd(d_h, x_res, mean, rstd, ln_w, dres=d_out, want_bf16=True)
+        _publish_bf16(dx, dx_b)
+        d_temb = None
+        if ctx.has_temb:
+            d_temb = ops.colsum_grouped(dx, meta.add_period, meta.add_div).view(1, meta.add_period, D)
+        return (dx, None, None, d_lnw, d_lnb, d_wqkv[:D], d_bqkv[:D], d_wqkv[D:2 * D], d_bqkv[D:2 * D],
+                d_wqkv[2 * D:], d_bqkv[2 * D:], d_ow, d_ob, d_temb)
+
+
+# ------------------------------------------------------------------------------------------
+# x + fc2(quick_gelu(fc1(LN(x))))      reference: modeling_image.py:129-134, :148-151; CLIPMLP
+# ------------------------------------------------------------------------------------------
+class MlpBlockFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, eps, cache, ln_w, ln_b, w1, b1, w2, b2):
+        w1b = bf16_weight(cache, "fc1", w1)
+        w2b = bf16_weight(cache, "fc2", w2)
+        h, mean, rstd = ops.layernorm_fwd(x, ln_w, ln_b, eps)
+        u = torch.empty((x.shape[0], w1.shape[0]), device=x.device, dtype=BF16)
+        a = ops.gemm(h, w1b, bias=b1.detach(), epilogue=EPI_GELU, aux_out=u)
+        out = ops.gemm(a, w2b, bias=b2.detach(), epilogue=EPI_RESID, aux_in=x, out_dtype=F32)
+        ctx.save_for_backward(x, mean, rstd, h, u, a, w1b, w2b, ln_w)
+        return out
+
+    @staticmethod
+    def backward(ctx, d_out):
+        x, mean, rstd, h, u, a, w1b, w2b, ln_w = ctx.saved_tensors
+        d_out = _contig(d_out)
+        d_out_b = _bf16_of(d_out)
+        d_w2 = ops.gemm(d_out_b, a, a_mn=True, b_mn=True, out_dtype=F32)
+        d_b2 = ops.colsum(d_out_b)
+        d_u = ops.gemm(d_out_b, w2b, b_mn=True, epilogue=EPI_DGELU, aux_in=u)         # (dY @ W2) * gelu'(u)
+        d_w1 = ops.gemm(d_u, h, a_mn=True, b_mn=True, out_dtype=F32)
+        d_b1 = ops.colsum(d_u)
+        d_h = ops.gemm(d_u, w1b, b_mn=True)
+        dx, dx_b, d_lnw, d_lnb = ops.layernorm_bwd(d_h, x, mean, rstd, ln_w, dres=d_out, want_bf16=True)
+        _publish_bf16(dx, dx_b)
+        return dx, None, None, d_lnw, d_lnb, d_w1, d_b1, d_w2, d_b2
+
+
+# ------------------------------------------------------------------------------------------
+# CLIPVisionEmbeddings + pre_layrnorm on the PRESENT samples only
+#   reference: video/modeling_video.py:42-51 (conv k = s = patch, CLS, + position), the
+#   5-D -> (b t) reshape of modeling_image.py:636-639 and pre_layrnorm at :649
+# ------------------------------------------------------------------------------------------
+class VisionEmbedFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, pixels, present_idx, n_present, geom, cache, cls, patch_w, pos, ln_w, ln_b):
+        ps, T, gh, gw, eps = geom
+        D = patch_w.shape[0]
+        K = patch_w.shape[1] * ps * ps
+        Kpad = (K + 7) // 8 * 8
+        P = gh * gw
+        wp = bf16_weight(cache, "patch", patch_w, cols_dst=Kpad)
+        patches = ops.patchify(pixels, ps, Kpad, T, sample_index=present_idx, n_samples=n_present)
+        n_img = n_present * T
+        tok = torch.empty((n_img * (P + 1), D), device=pixels.device, dtype=F32)
+        ops.gemm(patches, wp, out=tok, epilogue=EPI_PATCH, aux_in=pos.detach(), patch_P=P)
+        ops.cls_rows(cls.detach(), pos.detach(), tok, n_img, P + 1)
+        x0, mean, rstd = ops.layernorm_fwd(tok, ln_w, ln_b, eps, out_dtype=F32)
+        ctx.dims = (n_img, P, D, K, tuple(patch_w.shape))
+        ctx.save_for_backward(tok, mean, rstd, patches, ln_w)
+        return x0
+
+    @staticmethod
+    def backward(ctx, d_x0):
+        tok, mean, rstd, patches, ln_w = ctx.saved_tensors
+        n_img, P, D, K, wshape = ctx.dims
+        d_x0 = _contig(d_x0)
+        _GRAD_BF16.pop(d_x0.data_ptr(), None)
+        d_tok, _, d_lnw, d_lnb = ops.layernorm_bwd(d_x0, tok, mean, rstd, ln_w)
+        d_pos, d_patch = ops.embed_bwd(d_tok, n_img, P + 1)
+        d_w = ops.gemm(d_patch, patches, a_mn=True, b_mn=True, out_dtype=F32)          # [D, Kpad]
+        d_w = d_w[:, :K].reshape(wshape)
+        d_cls = d_pos[0].clone()
+        return None, None, None, None, None, d_cls, d_w, d_pos, d_lnw, d_lnb
+
+
+# ------------------------------------------------------------------------------------------
+# CLIPTextEmbeddings on the present samples   (modeling_image.py:463,494)
+# ------------------------------------------------------------------------------------------
+class TextEmbedFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, ids, present_idx, n_present, tok_emb, pos_emb):
+        L = ids.shape[1]
+        x0 = ops.text_embed_fwd(ids, tok_emb.detach(), pos_emb.detach()[:L], sample_index=present_idx,
+                                n_samples=n_present)
+        ctx.save_for_backward(ids, present_idx if present_idx is not None else ids.new_empty(0))
+        ctx.info = (n_present, tok_emb.shape[0], pos_emb.shape[0], present_idx is not None)
+        return x0
+
+    @staticmethod
+    def backward(ctx, d_x0):
+        ids, present_idx = ctx.saved_tensors
+        n_present, vocab, n_pos, has_idx = ctx.info
+        d_x0 = _contig(d_x0)
+        _GRAD_BF16.pop(d_x0.data_ptr(), None)
+        d_tok, d_pos_used = ops.text_embed_bwd(ids, d_x0, vocab, sample_index=present_idx if has_idx else None,
+                                               n_samples=n_present)
+        if d_pos_used.shape[0] != n_pos:
+            d_pos = torch.zeros((n_pos, d_pos_used.shape[1]), device=d_x0.device, dtype=F32)
+            d_pos[:d_pos_used.shape[0]] = d_pos_used
+        else:
+            d_pos = d_pos_used
+        return None, None, None, d_tok, d_pos
+
+
+# ------------------------------------------------------------------------------------------
+# pooled rows -> LayerNorm -> (frame mean) -> projection -> L2 normalise -> * exp(logit_scale)
+#   reference: modeling_image.py:658-662 (CLS, post_layernorm, mean over T), :514-522 (text:
+#   final_layer_norm + EOT row), languagebind/__init__.py:79-83
+# ------------------------------------------------------------------------------------------
+class PoolProjFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, rows, n_present, T, eps, scale, cache, ln_w, ln_b, proj_w):
+        wp = bf16_weight(cache, "proj", proj_w)
+        n_rows = n_present * T
+        if T == 1:
+            pooled_b, mean, rstd = ops.layernorm_fwd(x, ln_w, ln_b, eps, row_index=rows, n_rows=n_rows)
+        else:
+            pooled_f, mean, rstd = ops.layernorm_fwd(x, ln_w, ln_b, eps, out_dtype=F32, row_index=rows,
+                                                     n_rows=n_rows)
+            pooled_b = ops.frame_mean(pooled_f, n_present, T)
+        z = ops.gemm(pooled_b, wp, out_dtype=F32)
+        y, inv = ops.l2norm_scale_fwd(z, scale)
+        ctx.info = (n_present, T, scale)
+        ctx.save_for_backward(x, rows, mean, rstd, pooled_b, z, inv, wp, ln_w)
+        return y
+
+    @staticmethod
+    def backward(ctx, d_y):
+        x, rows, mean, rstd, pooled_b, z, inv, wp, ln_w = ctx.saved_tensors
+        n_present, T, scale = ctx.info
+        d_z = ops.l2norm_scale_bwd(_contig(d_y), z, inv, scale)                        # bf16 [Bp, P]
+        d_proj = ops.gemm(d_z, pooled_b, a_mn=True, b_mn=True, out_dtype=F32, split_k=1)
+        if T == 1:
+            d_pooled = ops.gemm(d_z, wp, b_mn=True)                                    # bf16
+        else:
+            d_pm = ops.gemm(d_z, wp, b_mn=True, out_dtype=F32)
+            d_pooled = ops.frame_mean_bwd(d_pm, n_present, T)                          # f32 [Bp*T, D]
+        dx = torch.zeros_like(x)
+        dx_b = torch.zeros(x.shape, device=x.device, dtype=BF16)
+        _, _, d_lnw, d_lnb = ops.layernorm_bwd(d_pooled, x, mean, rstd, ln_w, row_index=rows, dx=dx,
+                                                dx_bf16=dx_b)
+        _publish_bf16(dx, dx_b)
+        return dx, None, None, None, None, None, None, d_lnw, d_lnb, d_proj
+
+
+# ------------------------------------------------------------------------------------------
+# embeddings of the present samples back into batch order, zero rows for missing samples
+# ------------------------------------------------------------------------------------------
+class ScatterZeroFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, emb_present, slot_of, present_idx, n_present, B):
+        ctx.n = n_present
+        ctx.save_for_backward(present_idx)
+        return ops.scatter_rows_zero(emb_present, slot_of, B)
+
+    @staticmethod
+    def backward(ctx, d_out):
+        (present_idx,) = ctx.saved_tensors
+        return ops.gather_rows(_contig(d_out), present_idx, ctx.n), None, None, None, None

@@ -1,0 +1,127 @@
+"""The encoder bank: drop-in for `languagebind.LanguageBind` (languagebind/__init__.py:54-85)
+with missing-modality mask compaction in front of every tower."""
+import os
+
+import torch
+from torch import nn
+
+from . import autograd as ag
+from . import ops
+from . import towers as T
+from . import config as C
+
+# src/model/baseline.py:8 -- depth / thermal have no code in the reference; BASELINE.json configs 2
+# and 4 use those towers, so the map is extended without touching codes 0-4.
+MISSING_TYPE_INDEX = {'language': 1, 'video': 2, 'audio': 3, 'image': 4, 'depth': 5, 'thermal': 6}
+
+config_dict = {
+    'thermal': C.LanguageBindThermalConfig, 'image': C.LanguageBindImageConfig,
+    'video': C.LanguageBindVideoConfig, 'depth': C.LanguageBindDepthConfig,
+    'audio': C.LanguageBindAudioConfig,
+}
+model_dict = {
+    'thermal': T.LanguageBindThermal, 'image': T.LanguageBindImage, 'video': T.LanguageBindVideo,
+    'depth': T.LanguageBindDepth, 'audio': T.LanguageBindAudio,
+}
+
+
+class _ZeroTower(torch.autograd.Function):
+    """A tower that saw zero present samples on this rank still has to hand DDP a gradient for
+    every parameter (find_unused_parameters=False, train_ddp.py:189): emit zero embeddings whose
+    backward returns explicit zero gradients."""
+
+    @staticmethod
+    def forward(ctx, B, P, device, *params):
+        ctx.shapes = [p.shape for p in params]
+        ctx.dev = device
+        return torch.zeros((B, P), device=device, dtype=torch.float32)
+
+    @staticmethod
+    def backward(ctx, d_out):
+        return (None, None, None) + tuple(torch.zeros(s, device=ctx.dev, dtype=torch.float32) for s in ctx.shapes)
+
+
+class LanguageBind(nn.Module):
+    supports_compaction = True
+
+    def __init__(self, clip_type, use_temp=True, cache_dir='./cache_dir'):
+        super().__init__()
+        self.use_temp = use_temp
+        self.modality_encoder = {}
+        self.modality_proj = {}
+        self.modality_scale = {}
+        self.modality_config = {}
+        model = None
+        for k, v in clip_type.items():
+            pretrained_ckpt = f'LanguageBind/{v}'
+            model = model_dict[k].from_pretrained(pretrained_ckpt, cache_dir=cache_dir)
+            self.modality_encoder[k] = model.vision_model
+            self.modality_proj[k] = model.visual_projection
+            self.modality_scale[k] = model.logit_scale
+            self.modality_config[k] = model.config
+        # the text tower comes from the LAST loaded model (languagebind/__init__.py:69-70)
+        self.modality_encoder['language'] = model.text_model
+        self.modality_proj['language'] = model.text_projection
+        self.modality_encoder = nn.ModuleDict(self.modality_encoder)
+        self.modality_proj = nn.ModuleDict(self.modality_proj)
+        self.compaction = os.environ.get("MISSM_COMPACTION", "1") != "0"
+
+    @classmethod
+    def from_models(cls, models, use_temp=True):
+        """Build a bank from already constructed LanguageBind* models (dict modality -> model)."""
+        self = cls.__new__(cls)
+        nn.Module.__init__(self)
+        self.use_temp = use_temp
+        enc, proj, self.modality_scale, self.modality_config = {}, {}, {}, {}
+        model = None
+        for k, model in models.items():
+            enc[k], proj[k] = model.vision_model, model.visual_projection
+            self.modality_scale[k], self.modality_config[k] = model.logit_scale, model.config
+        enc['language'], proj['language'] = model.text_model, model.text_projection
+        self.modality_encoder, self.modality_proj = nn.ModuleDict(enc), nn.ModuleDict(proj)
+        self.compaction = os.environ.get("MISSM_COMPACTION", "1") != "0"
+        return self
+
+    def _scale(self, key):
+        if self.use_temp and key != 'language':
+            return float(self.modality_scale[key].detach().exp())
+        return 1.0
+
+    def forward(self, inputs, missing_index=None):
+        """inputs: {modal: {'pixel_values': ...} | {'input_ids', 'attention_mask'}} -> {modal: [B, P]}.
+        `missing_index` (int64 [B], optional) enables compaction: a tower only runs the samples whose
+        code differs from its own; rows of missing samples come back as zeros."""
+        ag.reset_side_channel()
+        keys = list(inputs.keys())
+        plan = {}
+        if missing_index is not None and self.compaction and len(keys) > 0:
+            mi = missing_index.reshape(-1).to(torch.int64).contiguous()
+            if not mi.is_cuda:
+                raise RuntimeError("missm_b200: missing_index must be on the CUDA device")
+            codes = [MISSING_TYPE_INDEX.get(k, -1) for k in keys]
+            idx, slot, counts = ops.compact_mask(mi, codes)
+            counts = counts.tolist()          # the one host sync of the step: sizes of the towers' batches
+            B = mi.numel()
+            for i, k in enumerate(keys):
+                if counts[i] < B:
+                    plan[k] = (idx[i], slot[i], counts[i], B)
+        outputs = {}
+        for key in keys:
+            value = inputs[key]
+            enc, proj = self.modality_encoder[key], self.modality_proj[key]
+            scale = self._scale(key)
+            if key in plan:
+                pidx, slot, n, B = plan[key]
+                if n == 0:
+                    params = [p for p in list(enc.parameters()) + list(proj.parameters())]
+                    outputs[key] = _ZeroTower.apply(B, proj.weight.shape[0], proj.weight.device, *params)
+                    continue
+                y = enc(**value, present_idx=pidx, n_present=n, proj=proj, scale=scale)[1]
+                outputs[key] = ag.ScatterZeroFn.apply(y, slot, pidx, n, B)
+            else:
+                outputs[key] = enc(**value, proj=proj, scale=scale)[1]
+        return outputs
+
+
+def to_device(x, device):
+    return {k: v.to(device) for k, v in x.items()}

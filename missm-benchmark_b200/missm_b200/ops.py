@@ -13,6 +13,11 @@ from ._lib import AttnArgs, GemmArgs, check, lib, stream_ptr
 EPI_LINEAR, EPI_GELU, EPI_RESID, EPI_DGELU, EPI_PATCH = range(5)
 BF16, F32 = torch.bfloat16, torch.float32
 
+# bookkeeping for bench.py: number of OUR kernels launched, and (optionally) CUDA-event pairs
+# around every GEMM launch on the launching stream: list of (start, end, flop)
+LAUNCHES = [0]
+GEMM_TIMING = None
+
 
 def _p(t):
     return ctypes.c_void_p(t.data_ptr()) if t is not None else None
@@ -53,6 +58,14 @@ def gemm(a, b, *, a_mn=False, b_mn=False, out=None, out_dtype=BF16, bias=None,
     g.out_f32 = int(out.dtype == F32)
     g.scale_cols, g.col_scale = scale_cols, col_scale
     g.patch_P, g.split_k, g.force_bn = patch_P, split_k, force_bn
+    LAUNCHES[0] += 1
+    if GEMM_TIMING is not None and M > 0:
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        check(lib().missm_gemm_bf16(ctypes.byref(g), stream_ptr()), "gemm_bf16")
+        e1.record()
+        GEMM_TIMING.append((e0, e1, 2.0 * M * N * K))
+        return out
     check(lib().missm_gemm_bf16(ctypes.byref(g), stream_ptr()), "gemm_bf16")
     return out
 
@@ -102,6 +115,7 @@ def attention_fwd(qkv, lay, H, *, causal=False, key_mask=None, mask_rows=None, m
     out = torch.empty((qkv.shape[0], D), device=qkv.device, dtype=BF16)
     lse = torch.empty((lay.n_seq, H, lay.N), device=qkv.device, dtype=F32)
     a = _attn_args(qkv, out, lse, lay, H, causal, key_mask, mask_rows, mask_div)
+    LAUNCHES[0] += 1
     check(lib().missm_attention_fwd(ctypes.byref(a), stream_ptr()), "attention_fwd")
     return out, lse
 
@@ -114,13 +128,14 @@ def attention_bwd(qkv, out, lse, d_out, lay, H, q_scale, *, causal=False, key_ma
     delta = torch.empty_like(lse)
     a = _attn_args(qkv, out, lse, lay, H, causal, key_mask, mask_rows, mask_div)
     a.d_out, a.delta, a.dqkv, a.q_scale = d_out.data_ptr(), delta.data_ptr(), dqkv.data_ptr(), q_scale
+    LAUNCHES[0] += 3
     check(lib().missm_attention_bwd(ctypes.byref(a), stream_ptr()), "attention_bwd")
     return dqkv
 
 
 # ---------------------------------------------------------------------------------- layernorm
 def layernorm_fwd(x, gamma, beta, eps, *, out_dtype=BF16, row_index=None, n_rows=None,
-                  add_rows=None, add_period=0, add_div=0, want_stats=True):
+                  add_rows=None, add_period=0, add_div=0, x_out=None, want_stats=True):
     """x f32 [R, D] -> (y [M, D], mean [M], rstd [M]); M = len(row_index) or R."""
     assert x.dtype == F32 and x.is_cuda
     D = x.shape[1]
@@ -128,8 +143,10 @@ def layernorm_fwd(x, gamma, beta, eps, *, out_dtype=BF16, row_index=None, n_rows
     y = torch.empty((M, D), device=x.device, dtype=out_dtype)
     mean = torch.empty((M,), device=x.device, dtype=F32) if want_stats else None
     rstd = torch.empty((M,), device=x.device, dtype=F32) if want_stats else None
+    LAUNCHES[0] += 1
     check(lib().missm_layernorm_fwd(_p(x), _ld(x), _p(row_index), _p(add_rows), add_period, add_div,
-                                    _p(x) if add_rows is not None else None, _p(gamma), _p(beta),
+                                    _p(x_out if x_out is not None else x) if add_rows is not None else None,
+                                    _p(gamma), _p(beta),
                                     _p(y), _ld(y), int(out_dtype == BF16), _p(mean), _p(rstd), M, D,
                                     eps, stream_ptr()), "layernorm_fwd")
     return y, mean, rstd
@@ -150,6 +167,7 @@ def layernorm_bwd(dy, x, mean, rstd, gamma, *, dres=None, row_index=None, dx=Non
     partial = torch.empty((nparts, 2, D), device=x.device, dtype=F32)
     dgamma = torch.empty((D,), device=x.device, dtype=F32)
     dbeta = torch.empty((D,), device=x.device, dtype=F32)
+    LAUNCHES[0] += 3
     check(lib().missm_layernorm_bwd(_p(dy), _ld(dy), int(dy.dtype == BF16), _p(x), _ld(x),
                                     _p(row_index), _p(mean), _p(rstd), _p(gamma), _p(dres), _p(dx),
                                     _p(dx_bf16), _p(partial), _p(dgamma), _p(dbeta), M, D,
@@ -165,6 +183,7 @@ def cast_bf16(src, out=None, cols_dst=None):
     cols_dst = cols if cols_dst is None else cols_dst
     if out is None:
         out = torch.empty((rows, cols_dst), device=src.device, dtype=BF16)
+    LAUNCHES[0] += 1
     check(lib().missm_cast_f32_bf16(_p(src), _ld(src), _p(out), _ld(out), rows, cols, cols_dst,
                                     stream_ptr()), "cast_f32_bf16")
     return out
@@ -177,22 +196,44 @@ def colsum(x):
     R = lib().missm_colsum_num_partials(M)
     partial = torch.empty((R, N), device=x.device, dtype=F32)
     out = torch.empty((N,), device=x.device, dtype=F32)
+    LAUNCHES[0] += 2
     check(lib().missm_colsum_bf16(_p(x), _ld(x), M, N, _p(partial), _p(out), stream_ptr()), "colsum")
     return out
 
 
-def patchify(pixels, ps, Kpad, sample_index=None, n_samples=None):
-    """pixels f32 [*, C, H, W] -> bf16 [Bn * gh * gw, Kpad] patches of the present samples."""
-    assert pixels.dtype == F32 and pixels.is_contiguous() and pixels.dim() == 4
-    _, C, H, W = pixels.shape
+def patchify(pixels, ps, Kpad, T=1, sample_index=None, n_samples=None):
+    """pixels f32 [*, C, H, W] (T = 1) or [*, C, T, H, W] -> bf16 [Bn * T * gh * gw, Kpad] patches of
+    the present samples."""
+    assert pixels.dtype == F32 and pixels.is_contiguous()
+    assert pixels.dim() == (4 if T == 1 else 5)
+    C, H, W = pixels.shape[1], pixels.shape[-2], pixels.shape[-1]
     Bn = n_samples if n_samples is not None else pixels.shape[0]
-    out = torch.empty((Bn * (H // ps) * (W // ps), Kpad), device=pixels.device, dtype=BF16)
-    check(lib().missm_patchify(_p(pixels), _p(sample_index), _p(out), Bn, C, H, W, ps, Kpad,
+    out = torch.empty((Bn * T * (H // ps) * (W // ps), Kpad), device=pixels.device, dtype=BF16)
+    LAUNCHES[0] += 2
+    check(lib().missm_patchify(_p(pixels), _p(sample_index), _p(out), Bn, C, T, H, W, ps, Kpad,
                                stream_ptr()), "patchify")
     return out
 
 
+def colsum_grouped(x, period, div):
+    """x f32 [M, D] -> f32 [period, D]: sums of the rows r with (r // div) % period == g."""
+    assert x.dtype == F32 and x.is_contiguous()
+    M, D = x.shape
+    out = torch.empty((period, D), device=x.device, dtype=F32)
+    LAUNCHES[0] += 1
+    check(lib().missm_colsum_grouped_f32(_p(x), M, D, period, div, _p(out), stream_ptr()), "colsum_grouped")
+    return out
+
+
+def copy_f32(src, dst):
+    assert src.dtype == F32 and dst.dtype == F32 and src.is_contiguous() and dst.is_contiguous()
+    assert src.numel() == dst.numel()
+    check(lib().missm_copy_f32(_p(src), _p(dst), src.numel(), stream_ptr()), "copy_f32")
+    return dst
+
+
 def cls_rows(cls, pos, tok, Bn, ntok):
+    LAUNCHES[0] += 1
     check(lib().missm_cls_rows(_p(cls), _p(pos), _p(tok), Bn, ntok, tok.shape[1], stream_ptr()), "cls_rows")
 
 
@@ -200,6 +241,7 @@ def embed_bwd(dtok, Bn, ntok):
     D = dtok.shape[1]
     dpos = torch.empty((ntok, D), device=dtok.device, dtype=F32)
     dpatch = torch.empty((Bn * (ntok - 1), D), device=dtok.device, dtype=BF16)
+    LAUNCHES[0] += 1
     check(lib().missm_embed_bwd(_p(dtok), _p(dpos), _p(dpatch), Bn, ntok, D, stream_ptr()), "embed_bwd")
     return dpos, dpatch
 
@@ -207,6 +249,7 @@ def embed_bwd(dtok, Bn, ntok):
 def frame_mean(x, Bn, T, out_dtype=BF16):
     D = x.shape[1]
     out = torch.empty((Bn, D), device=x.device, dtype=out_dtype)
+    LAUNCHES[0] += 1
     check(lib().missm_frame_mean(_p(x), _p(out), int(out_dtype == BF16), Bn, T, D, stream_ptr()), "frame_mean")
     return out
 
@@ -214,6 +257,7 @@ def frame_mean(x, Bn, T, out_dtype=BF16):
 def frame_mean_bwd(dout, Bn, T):
     D = dout.shape[1]
     din = torch.empty((Bn * T, D), device=dout.device, dtype=F32)
+    LAUNCHES[0] += 1
     check(lib().missm_frame_mean_bwd(_p(dout), _p(din), Bn, T, D, stream_ptr()), "frame_mean_bwd")
     return din
 
@@ -222,6 +266,7 @@ def l2norm_scale_fwd(x, scale):
     Bn, P = x.shape
     y = torch.empty_like(x)
     inv = torch.empty((Bn,), device=x.device, dtype=F32)
+    LAUNCHES[0] += 1
     check(lib().missm_l2norm_scale_fwd(_p(x), _p(y), _p(inv), scale, Bn, P, stream_ptr()), "l2norm_fwd")
     return y, inv
 
@@ -229,6 +274,7 @@ def l2norm_scale_fwd(x, scale):
 def l2norm_scale_bwd(dy, x, inv, scale, out_dtype=BF16):
     Bn, P = x.shape
     dx = torch.empty((Bn, P), device=x.device, dtype=out_dtype)
+    LAUNCHES[0] += 1
     check(lib().missm_l2norm_scale_bwd(_p(dy), _p(x), _p(inv), scale, _p(dx), int(out_dtype == BF16),
                                        Bn, P, stream_ptr()), "l2norm_bwd")
     return dx
@@ -240,6 +286,7 @@ def text_embed_fwd(ids, tok_emb, pos_emb, sample_index=None, n_samples=None):
     Bn = n_samples if n_samples is not None else ids.shape[0]
     D = tok_emb.shape[1]
     out = torch.empty((Bn * L, D), device=ids.device, dtype=F32)
+    LAUNCHES[0] += 1
     check(lib().missm_text_embed_fwd(_p(ids), _p(sample_index), _p(tok_emb), _p(pos_emb), _p(out), Bn,
                                      L, D, stream_ptr()), "text_embed_fwd")
     return out
@@ -251,6 +298,7 @@ def text_embed_bwd(ids, dx, vocab, sample_index=None, n_samples=None):
     D = dx.shape[1]
     dtok = torch.zeros((vocab, D), device=dx.device, dtype=F32)
     dpos = torch.empty((L, D), device=dx.device, dtype=F32)
+    LAUNCHES[0] += 1
     check(lib().missm_text_embed_bwd(_p(ids), _p(sample_index), _p(dx), _p(dtok), _p(dpos), Bn, L, D,
                                      stream_ptr()), "text_embed_bwd")
     return dtok, dpos
@@ -260,6 +308,7 @@ def argmax_rows(ids, sample_index=None, n_samples=None):
     L = ids.shape[1]
     Bn = n_samples if n_samples is not None else ids.shape[0]
     out = torch.empty((Bn,), device=ids.device, dtype=torch.int32)
+    LAUNCHES[0] += 1
     check(lib().missm_argmax_rows(_p(ids), _p(sample_index), _p(out), Bn, L, stream_ptr()), "argmax_rows")
     return out
 
@@ -275,6 +324,7 @@ def compact_mask(missing_index, codes):
     slot = torch.empty((T, B), device=dev, dtype=torch.int32)
     counts = torch.empty((T,), device=dev, dtype=torch.int32)
     codes_host = (ctypes.c_int32 * T)(*[int(c) for c in codes])
+    LAUNCHES[0] += 1
     check(lib().missm_compact_mask(_p(missing_index), B, ctypes.cast(codes_host, ctypes.c_void_p), T,
                                    _p(idx), _p(slot), _p(counts), stream_ptr()), "compact_mask")
     return idx, slot, counts
@@ -283,6 +333,7 @@ def compact_mask(missing_index, codes):
 def scatter_rows_zero(src, slot_of, B):
     P = src.shape[1]
     dst = torch.empty((B, P), device=slot_of.device, dtype=F32)
+    LAUNCHES[0] += 1
     check(lib().missm_scatter_rows_zero(_p(src), _p(slot_of), _p(dst), B, P, stream_ptr()), "scatter_rows_zero")
     return dst
 
@@ -292,5 +343,6 @@ def gather_rows(src, idx, n_rows):
     assert src.is_contiguous()
     row_bytes = src.stride(0) * src.element_size()
     dst = torch.empty((n_rows,) + tuple(src.shape[1:]), device=src.device, dtype=src.dtype)
+    LAUNCHES[0] += 1
     check(lib().missm_gather_rows(_p(src), _p(idx), _p(dst), n_rows, row_bytes, stream_ptr()), "gather_rows")
     return dst

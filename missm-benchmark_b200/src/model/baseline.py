@@ -1,0 +1,267 @@
+"""Drop-in `src.model.baseline`: `finetune_model` and the missing-modality fusion heads with the
+reference's parameter names (so `final_model/<ds>_<fusion>.pth` files load, test.py:92), the
+same constructor arguments (`args.fusion_type, modality_types, feature_dims, fusion_dim,
+dropout_prob`), the same return arity per fusion type (train_ddp.py:109-112,232-249) and the
+`fusion.set_statistics` hook (test.py:115).
+
+Reference: src/model/baseline.py -- Head :27-39, modal_sum :43-61, modal_concat :65-90,
+modal_regression :94-149, modal_concat_full :153-169, modal_intra_channel_attention :173-203,
+modal_inter_attention :207-236, modal_dedicated_dnn :335-354, modal_distillation :358-380,
+modal_self_distillation :384-418, finetune_model :421-453.  `graph_fusion` / `unified_graph`
+need torch_geometric.SuperGATConv and are not skip-safe: out of scope.
+
+The towers (>99.9 % of the step) run the hand-written CUDA path; `finetune_model.forward` hands
+`missing_index` to the encoder bank so that a tower only computes its PRESENT samples.  The
+default head (`sum`) runs the fused masked-fusion CUDA kernels of csrc/fusion.cu; the other heads
+are a handful of [B, <=1536] tensor ops expressed with torch.nn (library kernels).
+"""
+import torch
+from torch import nn
+
+from languagebind import LanguageBind, to_device, transform_dict, LanguageBindImageTokenizer  # noqa: F401
+from missm_b200.bank import MISSING_TYPE_INDEX
+from missm_b200 import fusion_ops
+
+missing_type_index = MISSING_TYPE_INDEX
+
+
+def _miss(missing_index, modal):
+    return missing_index == missing_type_index[modal]
+
+
+class Head(nn.Module):
+    def __init__(self, args, input_dims, output_dims):
+        super().__init__()
+        self.head = nn.Sequential(
+            nn.Linear(input_dims, args.fusion_dim),
+            nn.ReLU(inplace=True),
+            nn.Dropout(args.dropout_prob),
+            nn.Linear(args.fusion_dim, output_dims),
+        )
+
+    def forward(self, inputs):
+        return self.head(inputs)
+
+
+class modal_sum(nn.Module):
+    def __init__(self, args, output_dims):
+        super().__init__()
+        self.modality_types = args.modality_types
+        self.modal_proj = nn.ModuleDict({m: nn.Linear(args.feature_dims, args.fusion_dim) for m in args.modality_types})
+        self.norm = nn.LayerNorm(args.fusion_dim)
+        self.head = Head(args, args.fusion_dim, output_dims)
+
+    def forward(self, batch, missing_index):
+        # fused: per-modality Linear, zero rows of missing samples, sum, LayerNorm  (:52-61)
+        fused = fusion_ops.masked_sum_norm(
+            [batch[m] for m in self.modality_types],
+            [self.modal_proj[m].weight for m in self.modality_types],
+            [self.modal_proj[m].bias for m in self.modality_types],
+            [missing_type_index[m] for m in self.modality_types],
+            missing_index, self.norm.weight, self.norm.bias, self.norm.eps)
+        return self.head(fused)
+
+
+class modal_concat(nn.Module):
+    def __init__(self, args, output_dims):
+        super().__init__()
+        self.modality_types = args.modality_types
+        n = len(args.modality_types)
+        self.modal_proj = nn.ModuleDict({m: nn.Linear(args.feature_dims, args.fusion_dim) for m in args.modality_types})
+        self.norm = nn.LayerNorm(args.fusion_dim * n)
+        self.head = Head(args, args.fusion_dim * n, output_dims)
+        for m in self.modality_types:
+            self.register_buffer(f'statistics_{m}', torch.zeros(args.feature_dims, dtype=torch.float))
+
+    def forward(self, batch, missing_index):
+        inputs = []
+        for m in self.modality_types:
+            stat = self.get_buffer(f'statistics_{m}').to(batch[m].device)
+            x = torch.where(_miss(missing_index, m)[:, None], stat[None, :].to(batch[m].dtype), batch[m])
+            inputs.append(self.modal_proj[m](x))
+        return self.head(self.norm(torch.cat(inputs, dim=-1)))
+
+    def set_statistics(self, statistics, modality_types):
+        for m in modality_types:
+            self.register_buffer(f'statistics_{m}', torch.as_tensor(statistics[m], dtype=torch.float,
+                                                                    device=self.modal_proj[m].weight.device))
+
+
+class modal_regression(nn.Module):
+    def __init__(self, args, output_dims):
+        super().__init__()
+        self.modality_types = args.modality_types
+        n = len(args.modality_types)
+        self.modal_proj = nn.ModuleDict({m: nn.Linear(args.feature_dims, args.fusion_dim) for m in args.modality_types})
+        self.norm = nn.LayerNorm(args.fusion_dim * n)
+        self.head = Head(args, args.fusion_dim * n, output_dims)
+        self.cross_modal_regressors = nn.ModuleDict()
+        for s in self.modality_types:
+            for t in self.modality_types:
+                if s != t:
+                    self.cross_modal_regressors[f"{s}_to_{t}"] = nn.Linear(args.feature_dims, args.fusion_dim)
+
+    def forward(self, batch, missing_index):
+        pf = {m: self.modal_proj[m](batch[m]) for m in self.modality_types}
+        for t in self.modality_types:
+            tmask = _miss(missing_index, t)
+            preds, masks = [], []
+            for s in self.modality_types:
+                if s != t:
+                    preds.append(self.cross_modal_regressors[f"{s}_to_{t}"](batch[s]))
+                    masks.append((~_miss(missing_index, s)).to(preds[-1].dtype))
+            preds = torch.stack(preds, dim=1)
+            masks = torch.stack(masks, dim=-1).unsqueeze(-1)
+            avg = (preds * masks).sum(dim=1) / masks.sum(dim=1).clamp(min=1e-6)
+            pf[t] = torch.where(tmask[:, None], avg, pf[t])
+        return self.head(self.norm(torch.cat([pf[m] for m in self.modality_types], dim=-1)))
+
+
+class modal_concat_full(nn.Module):
+    def __init__(self, args, output_dims):
+        super().__init__()
+        self.modality_types = args.modality_types
+        n = len(args.modality_types)
+        self.modal_proj = nn.ModuleDict({m: nn.Linear(args.feature_dims, args.fusion_dim) for m in args.modality_types})
+        self.norm = nn.LayerNorm(args.fusion_dim * n)
+        self.head = Head(args, args.fusion_dim * n, output_dims)
+
+    def forward(self, batch, missing_index):
+        return self.head(self.norm(torch.cat([self.modal_proj[m](batch[m]) for m in self.modality_types], dim=-1)))
+
+
+class modal_intra_channel_attention(nn.Module):
+    def __init__(self, args, output_dims):
+        super().__init__()
+        self.modality_types = args.modality_types
+        self.modal_proj = nn.ModuleDict({m: nn.Linear(args.feature_dims, args.fusion_dim) for m in args.modality_types})
+        self.norm = nn.LayerNorm(args.fusion_dim)
+        self.head = Head(args, args.fusion_dim, output_dims)
+        self.fusion_representation = nn.Parameter(torch.randn(1, args.fusion_dim))
+        self.channel_attention = nn.Sequential(
+            nn.Linear(args.fusion_dim * 2, args.fusion_dim // 4), nn.ReLU(),
+            nn.Linear(args.fusion_dim // 4, args.fusion_dim), nn.Sigmoid())
+
+    def forward(self, batch, missing_index):
+        total = 0
+        for m in self.modality_types:
+            d = self.modal_proj[m](batch[m])
+            ca = self.channel_attention(torch.cat([d, self.fusion_representation.expand(d.shape[0], -1)], dim=-1))
+            d = d * ca
+            total = total + torch.where(_miss(missing_index, m)[:, None], torch.zeros_like(d), d)
+        return self.head(self.norm(total))
+
+
+class modal_inter_attention(nn.Module):
+    def __init__(self, args, output_dims):
+        super().__init__()
+        self.modality_types = args.modality_types
+        self.modal_proj = nn.ModuleDict({m: nn.Linear(args.feature_dims, args.fusion_dim) for m in args.modality_types})
+        self.norm = nn.LayerNorm(args.fusion_dim)
+        self.head = Head(args, args.fusion_dim, output_dims)
+        self.query_token = nn.Parameter(torch.randn(1, 1, args.fusion_dim))
+        self.attn = nn.MultiheadAttention(args.fusion_dim, num_heads=4, batch_first=True)
+
+    def forward(self, batch, missing_index):
+        toks = torch.stack([self.modal_proj[m](batch[m]) for m in self.modality_types], dim=1)
+        mask = torch.stack([_miss(missing_index, m) for m in self.modality_types], dim=1)
+        query = self.query_token.expand(toks.shape[0], -1, -1)
+        out, _ = self.attn(query, toks, toks, key_padding_mask=mask.bool())
+        return self.head(self.norm(out[:, 0, :]))
+
+
+class modal_dedicated_dnn(nn.Module):
+    def __init__(self, args, output_dims):
+        super().__init__()
+        self.modality_types = args.modality_types
+        n = len(self.modality_types)
+        d = {m: nn.Linear(args.feature_dims * (n - 1), args.fusion_dim) for m in args.modality_types}
+        d['full'] = nn.Linear(args.feature_dims * n, args.fusion_dim)
+        self.dedicated_dnn = nn.ModuleDict(d)
+        self.norm = nn.LayerNorm(args.fusion_dim)
+        self.head = Head(args, args.fusion_dim, output_dims)
+
+    def forward(self, batch, missing_index):
+        feats = torch.stack([batch[m] for m in self.modality_types], dim=1)
+        B = feats.shape[0]
+        out = self.dedicated_dnn['full'](feats.view(B, -1))
+        for i, m in enumerate(self.modality_types):
+            alt = self.dedicated_dnn[m](torch.cat([feats[:, :i], feats[:, i + 1:]], dim=1).view(B, -1))
+            out = torch.where(_miss(missing_index, m)[:, None], alt, out)
+        return self.head(self.norm(out))
+
+
+def _zeroed(batch, missing_index, modality_types):
+    return [torch.where(_miss(missing_index, m)[:, None], torch.zeros_like(batch[m]), batch[m])
+            for m in modality_types]
+
+
+class modal_distillation(nn.Module):
+    def __init__(self, args, output_dims):
+        super().__init__()
+        self.modality_types = args.modality_types
+        n = len(self.modality_types)
+        self.modal_proj = nn.Sequential(nn.Linear(args.feature_dims * n, args.fusion_dim), nn.ReLU(),
+                                        nn.Linear(args.fusion_dim, args.fusion_dim))
+        self.norm = nn.LayerNorm(args.fusion_dim)
+        self.head = Head(args, args.fusion_dim, output_dims)
+
+    def forward(self, batch, missing_index):
+        features = torch.cat(_zeroed(batch, missing_index, self.modality_types), dim=-1)
+        return features, self.head(self.norm(self.modal_proj(features)))
+
+
+class modal_self_distillation(nn.Module):
+    def __init__(self, args, output_dims):
+        super().__init__()
+        self.modality_types = args.modality_types
+        n = len(self.modality_types)
+        self.modal_proj = nn.Sequential(nn.Linear(args.feature_dims * n, args.fusion_dim), nn.ReLU(),
+                                        nn.Linear(args.fusion_dim, args.fusion_dim))
+        self.norm = nn.LayerNorm(args.fusion_dim)
+        self.head = Head(args, args.fusion_dim, output_dims)
+
+    def forward(self, batch, missing_index):
+        ori = _zeroed(batch, missing_index, self.modality_types)
+        if not self.training:
+            return self.head(self.norm(self.modal_proj(torch.cat(ori, dim=-1))))
+        B, Cd = ori[0].shape
+        n = len(self.modality_types)
+        stu, masks = [], []
+        for i, m in enumerate(self.modality_types):
+            z = torch.cat([ori[i].new_zeros((B, i * Cd)), ori[i], ori[i].new_zeros((B, (n - i - 1) * Cd))], dim=-1)
+            stu.append(self.modal_proj(z))
+            masks.append(missing_index != missing_type_index[m])
+        tea = self.modal_proj(torch.cat(ori, dim=-1))
+        return masks, stu, tea, self.head(self.norm(tea))
+
+
+_FUSIONS = {
+    'sum': modal_sum, 'concat': modal_concat, 'regression': modal_regression, 'retrieval': modal_concat_full,
+    'intra_attention': modal_intra_channel_attention, 'inter_attention': modal_inter_attention,
+    'dedicated_dnn': modal_dedicated_dnn, 'Distill_tea': modal_distillation, 'MTD_stu': modal_distillation,
+    'KL_stu': modal_distillation, 'self_distill': modal_self_distillation,
+}
+
+
+class finetune_model(nn.Module):
+    def __init__(self, args, output_dims, encoder_model):
+        super().__init__()
+        self.encoder = encoder_model
+        self.fusion_type = args.fusion_type
+        if args.fusion_type in ('graph_fusion', 'unified_graph'):
+            raise NotImplementedError(
+                f"fusion_type={args.fusion_type!r} needs torch_geometric.SuperGATConv and is not skip-safe "
+                f"(reference baseline.py:240-331); out of scope of the B200 hot path (SURVEY.md 8(f) rank 4)")
+        if args.fusion_type not in _FUSIONS:
+            raise ValueError(f"unknown fusion_type {args.fusion_type!r}")
+        self.fusion = _FUSIONS[args.fusion_type](args, output_dims)
+
+    def forward(self, data, missing_index):
+        # `retrieval` ignores missing_index (the loader substituted a same-label sample and reset the
+        # code to 0, data_loader.py:271-276), so nothing may be skipped for it
+        if getattr(self.encoder, 'supports_compaction', False) and self.fusion_type != 'retrieval':
+            embedding = self.encoder(data, missing_index=missing_index)   # towers skip missing samples
+        else:
+            embedding = self.encoder(data)
+        return self.fusion(embedding, missing_index)

@@ -201,6 +201,11 @@ def test_cast_colsum_patchify(ops):
     px = torch.randn(5, 3, 28, 70, device=DEV)
     idx = torch.tensor([4, 0, 2], device=DEV, dtype=torch.int32)
     pt = ops.patchify(px, 14, 592, sample_index=idx, n_samples=3)
+    vid = torch.randn(4, 3, 2, 28, 28, device=DEV)
+    pv = ops.patchify(vid, 14, 592, T=2, sample_index=idx[:2] % 4, n_samples=2)
+    fr = vid[(idx[:2] % 4).long()].permute(0, 2, 1, 3, 4).reshape(4, 3, 28, 28)
+    rv = torch.nn.functional.unfold(fr, kernel_size=14, stride=14).transpose(1, 2).reshape(-1, 588)
+    assert torch.equal(pv[:, :588], rv.bfloat16())
     ref = torch.nn.functional.unfold(px[idx.long()], kernel_size=14, stride=14).transpose(1, 2).reshape(-1, 588)
     assert torch.equal(pt[:, :588], ref.bfloat16()) and (pt[:, 588:] == 0).all()
 
