@@ -67,13 +67,21 @@ colsum_bf16_kernel(const __nv_bfloat16* __restrict__ x, long ldx, int M, int N,
   }
 }
 
-__global__ void reduce_rows_kernel(const float* __restrict__ partial, int R, int N,
-                                   float* __restrict__ out) {
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= N) return;
+__global__ void __launch_bounds__(256)
+reduce_rows_kernel(const float* __restrict__ partial, int R, int N, float* __restrict__ out) {
+  __shared__ float red[8][33];
+  const int c = blockIdx.x * 32 + threadIdx.x;
   float s = 0.f;
-  for (int r = 0; r < R; ++r) s += partial[static_cast<long>(r) * N + c];
-  out[c] = s;
+  if (c < N)
+    for (int r = threadIdx.y; r < R; r += 8) s += partial[static_cast<long>(r) * N + c];
+  red[threadIdx.y][threadIdx.x] = s;
+  __syncthreads();
+  if (threadIdx.y == 0 && c < N) {
+    float t = 0.f;
+#pragma unroll
+    for (int y = 0; y < 8; ++y) t += red[y][threadIdx.x];
+    out[c] = t;
+  }
 }
 
 // ---------------------------------------------------------------------------------------
@@ -326,7 +334,7 @@ extern "C" int missm_colsum_bf16(const void* x, int64_t ldx, int32_t M, int32_t 
   dim3 grid((N + 255) / 256, R), block(32, kColsumRows);
   colsum_bf16_kernel<<<grid, block, 0, ST(stream)>>>(static_cast<const __nv_bfloat16*>(x), ldx, M, N,
                                                     partial, rows_per_block);
-  reduce_rows_kernel<<<(N + 127) / 128, 128, 0, ST(stream)>>>(partial, R, N, out);
+  reduce_rows_kernel<<<(N + 31) / 32, dim3(32, 8), 0, ST(stream)>>>(partial, R, N, out);
   MISSM_CHECK_CUDA(cudaGetLastError());
   return 0;
 }

@@ -2,11 +2,12 @@
 //
 //   C[m,n] = epilogue( sum_k A[m,k] * B[n,k] ),  bf16 operands, fp32 accumulation in TMEM.
 //
-// Roles per CTA (256 threads, one CTA per SM, persistent over work units):
+// Roles per CTA (384 threads, one CTA per SM, persistent over work units):
 //   warp 0 (1 lane) : TMA producer   global -> 128B-swizzled smem ring, mbarrier complete_tx
 //   warp 1 (1 lane) : MMA issuer     tcgen05.mma kind::f16, 128 x BN x 16 per instruction
 //   warp 2          : TMEM allocator
-//   warps 4..7      : epilogue       tcgen05.ld (32 lanes x 32 cols) -> fused epilogue -> HBM
+//   warps 4..11     : epilogue       tcgen05.ld (32 lanes x 32 cols) -> fused epilogue -> HBM
+//                     (two warps per TMEM lane quarter, alternating 32-column chunks)
 // Accumulators are double-buffered in TMEM (2 x BN columns) so the epilogue of tile i overlaps
 // the main loop of tile i+1.  Operands may be K-major or MN-major in memory (the "transpose"
 // of dgrad / wgrad is expressed in the UMMA descriptors, never materialised).
@@ -23,7 +24,8 @@ namespace missm {
 
 constexpr int BM = 128;
 constexpr int BK = 64;  // 64 bf16 = one 128-byte swizzle row
-constexpr int kGemmThreads = 256;
+constexpr int kEpiWarps = 8;                         // two per TMEM lane quarter
+constexpr int kGemmThreads = 128 + 32 * kEpiWarps;  // 4 control warps + epilogue warps
 constexpr int A_STAGE_BYTES = BM * BK * 2;
 
 struct GemmParams {
@@ -205,7 +207,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA,
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tfull_bar[i], 1);
-      mbar_init(&tempty_bar[i], 4);  // one arrive per epilogue warp
+      mbar_init(&tempty_bar[i], kEpiWarps);  // one arrive per epilogue warp
     }
     fence_mbar_init();
   }
@@ -296,7 +298,8 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA,
     }
   } else if (warp >= 4) {
     // ================================ epilogue ========================================
-    const int q = warp & 3;  // TMEM lane quarter this warp may access
+    const int q = warp & 3;               // TMEM lane quarter this warp may access
+    const int half = (warp - 4) >> 2;     // the two warps of a quarter split the column chunks
     int acc = 0;
     uint32_t acc_phase = 0;
     for (int w = blockIdx.x; w < total_work; w += gridDim.x) {
@@ -307,7 +310,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA,
       const int row = m_blk * BM + q * 32 + lane;
       const uint32_t t_row = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * BN;
 #pragma unroll 1
-      for (int c = 0; c < BN / 32; ++c) {
+      for (int c = half; c < BN / 32; c += kEpiWarps / 4) {
         const int col0 = n_blk * BN + c * 32;
         if (col0 >= p.N) break;  // warp-uniform
         uint32_t r[32];

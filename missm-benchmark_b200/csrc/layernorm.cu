@@ -162,13 +162,23 @@ layernorm_bwd_kernel(const void* __restrict__ dy, long lddy, const float* __rest
 }
 
 // out[c] = sum_r partial[r][c]    (deterministic second stage of column reductions)
-__global__ void reduce_partials_kernel(const float* __restrict__ partial, int R, long stride,
-                                       float* __restrict__ out, int n, float scale) {
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= n) return;
+// block = 32 columns x 8 row-threads: coalesced 128 B row segments, fixed summation order
+__global__ void __launch_bounds__(256)
+reduce_partials_kernel(const float* __restrict__ partial, int R, long stride,
+                       float* __restrict__ out, int n, float scale) {
+  __shared__ float red[8][33];
+  const int c = blockIdx.x * 32 + threadIdx.x;
   float s = 0.f;
-  for (int r = 0; r < R; ++r) s += partial[r * stride + c];
-  out[c] = s * scale;
+  if (c < n)
+    for (int r = threadIdx.y; r < R; r += 8) s += partial[r * stride + c];
+  red[threadIdx.y][threadIdx.x] = s;
+  __syncthreads();
+  if (threadIdx.y == 0 && c < n) {
+    float t = 0.f;
+#pragma unroll
+    for (int y = 0; y < 8; ++y) t += red[y][threadIdx.x];
+    out[c] = t * scale;
+  }
 }
 
 template <bool OUT_BF16>
@@ -219,7 +229,7 @@ using namespace missm;
 
 extern "C" int missm_ln_bwd_num_partials(int M) {
   int blocks = (M + kLnWarps - 1) / kLnWarps;
-  int cap = 2 * kNumSMs;
+  int cap = kNumSMs;
   return blocks < cap ? (blocks < 1 ? 1 : blocks) : cap;
 }
 
@@ -265,17 +275,19 @@ extern "C" int missm_layernorm_bwd(const void* dy, int64_t lddy, int32_t dy_bf16
     rc = launch_ln_bwd<false>(D / 128, grid, st, dy, lddy, x, ldx, row_index, mean, rstd, gamma,
                               dres, dx, static_cast<__nv_bfloat16*>(dx_bf16), partial, M);
   if (rc) return rc;
-  const int tb = 128;
-  reduce_partials_kernel<<<(D + tb - 1) / tb, tb, 0, st>>>(partial, grid, 2L * D, dgamma, D, 1.f);
-  reduce_partials_kernel<<<(D + tb - 1) / tb, tb, 0, st>>>(partial + D, grid, 2L * D, dbeta, D, 1.f);
+  if (dbeta == dgamma + D) {  // contiguous [2, D] output: one launch
+    reduce_partials_kernel<<<(2 * D + 31) / 32, dim3(32, 8), 0, st>>>(partial, grid, 2L * D, dgamma, 2 * D, 1.f);
+  } else {
+    reduce_partials_kernel<<<(D + 31) / 32, dim3(32, 8), 0, st>>>(partial, grid, 2L * D, dgamma, D, 1.f);
+    reduce_partials_kernel<<<(D + 31) / 32, dim3(32, 8), 0, st>>>(partial + D, grid, 2L * D, dbeta, D, 1.f);
+  }
   MISSM_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
 
 extern "C" int missm_reduce_partials(const float* partial, int32_t R, int64_t stride, float* out,
                                      int32_t n, float scale, void* stream) {
-  const int tb = 128;
-  reduce_partials_kernel<<<(n + tb - 1) / tb, tb, 0, static_cast<cudaStream_t>(stream)>>>(
+  reduce_partials_kernel<<<(n + 31) / 32, dim3(32, 8), 0, static_cast<cudaStream_t>(stream)>>>(
       partial, R, stride, out, n, scale);
   MISSM_CHECK_CUDA(cudaGetLastError());
   return 0;

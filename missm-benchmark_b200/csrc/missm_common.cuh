@@ -60,13 +60,19 @@ __device__ __forceinline__ float2 unpack_bf16x2(uint32_t u) {
   return __bfloat1622float2(v);
 }
 
-// QuickGELU (transformers ACT2FN["quick_gelu"]): x * sigmoid(1.702 x)
-__device__ __forceinline__ float quick_gelu(float x) {
-  return x / (1.0f + __expf(-1.702f * x));
+// QuickGELU (transformers ACT2FN["quick_gelu"]): x * sigmoid(1.702 x).
+// sigmoid(y) = 0.5 + 0.5 tanh(y/2): ONE MUFU op (tanh.approx.f32, rel. error 2^-11, far below the
+// bf16 rounding of the stored result) instead of ex2 + rcp -- the GEMM epilogues that apply it
+// run 32 K elements per tile and were MUFU/issue bound.
+__device__ __forceinline__ float fast_sigmoid_1702(float x) {
+  float t;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(0.851f * x));
+  return fmaf(0.5f, t, 0.5f);
 }
+__device__ __forceinline__ float quick_gelu(float x) { return x * fast_sigmoid_1702(x); }
 __device__ __forceinline__ float quick_gelu_grad(float x) {
-  float s = 1.0f / (1.0f + __expf(-1.702f * x));
-  return s * (1.0f + 1.702f * x * (1.0f - s));
+  const float s = fast_sigmoid_1702(x);
+  return fmaf(1.702f * x * s, 1.0f - s, s);
 }
 
 // ----------------------------------------------------------------------------------------

@@ -165,9 +165,9 @@ def layernorm_bwd(dy, x, mean, rstd, gamma, *, dres=None, row_index=None, dx=Non
         dx_bf16 = torch.empty(x.shape, device=x.device, dtype=BF16)
     nparts = lib().missm_ln_bwd_num_partials(M)
     partial = torch.empty((nparts, 2, D), device=x.device, dtype=F32)
-    dgamma = torch.empty((D,), device=x.device, dtype=F32)
-    dbeta = torch.empty((D,), device=x.device, dtype=F32)
-    LAUNCHES[0] += 3
+    dgb = torch.empty((2, D), device=x.device, dtype=F32)
+    dgamma, dbeta = dgb[0], dgb[1]
+    LAUNCHES[0] += 2
     check(lib().missm_layernorm_bwd(_p(dy), _ld(dy), int(dy.dtype == BF16), _p(x), _ld(x),
                                     _p(row_index), _p(mean), _p(rstd), _p(gamma), _p(dres), _p(dx),
                                     _p(dx_bf16), _p(partial), _p(dgamma), _p(dbeta), M, D,

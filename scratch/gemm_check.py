@@ -85,8 +85,23 @@ def bench(M, N, K, a_mn=False, b_mn=False, bn=0, iters=20, **kw):
     tf = 2 * M * N * K / ms / 1e9
     print(f"time M{M} N{N} K{K} a_mn={int(a_mn)} b_mn={int(b_mn)} bn={bn}: {ms:.3f} ms {tf:.0f} TF/s" + (f" (cublas {2*M*N*K/ref_ms/1e9:.0f})" if ref_ms else ""), flush=True)
 
-Mt = 64 * 257
-for bn in (128, 256):
+Mt = 58 * 257
+def bench_epi(name, **kw):
+    M, N, K = Mt, 4096, 1024
+    A = torch.randn(M, K, device=dev).bfloat16(); B = torch.randn(N, K, device=dev).bfloat16()
+    out = torch.empty(M, N, device=dev, dtype=torch.bfloat16)
+    for _ in range(3): ops.gemm(A, B, out=out, **kw)
+    e0, e1 = torch.cuda.Event(True), torch.cuda.Event(True)
+    e0.record()
+    for _ in range(20): ops.gemm(A, B, out=out, **kw)
+    e1.record(); torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / 20
+    print(f"time epi {name}: {ms:.3f} ms {2*M*N*K/ms/1e9:.0f} TF/s", flush=True)
+ub = torch.randn(Mt, 4096, device=dev).bfloat16()
+bench_epi("plain")
+bench_epi("gelu", bias=torch.randn(4096, device=dev), epilogue=ops.EPI_GELU, aux_out=torch.empty_like(ub))
+bench_epi("dgelu", epilogue=ops.EPI_DGELU, aux_in=ub)
+for bn in (256,):
     bench(Mt, 3072, 1024, bn=bn); bench(Mt, 1024, 1024, bn=bn); bench(Mt, 4096, 1024, bn=bn); bench(Mt, 1024, 4096, bn=bn)
 bench(8192, 8192, 8192, bn=256)
 bench(Mt, 1024, 4096, b_mn=True)
