@@ -104,13 +104,16 @@ __device__ __forceinline__ void load_a_frags(uint32_t (&f)[4][4], const __nv_bfl
 }
 
 // acc[16 x 64] += A[16 x 64(k)] * T^T where the tile T is stored [n = 64][k = 64]  ("n-major rows")
+// `npairs` (1..4, warp-uniform) = number of 16-row groups of the tile that hold valid rows: ragged
+// sequence tails (N = 257 = 4*64 + 1) skip the all-padding groups instead of multiplying zeros.
 __device__ __forceinline__ void mma_a_tileT(float (&acc)[8][4], const uint32_t (&a)[4][4],
-                                            const __nv_bfloat16* stile, int lane) {
+                                            const __nv_bfloat16* stile, int lane, int npairs) {
   const int m = lane >> 3, r = lane & 7;
 #pragma unroll
   for (int kk = 0; kk < 4; ++kk) {
 #pragma unroll
     for (int np = 0; np < 4; ++np) {
+      if (np >= npairs) continue;
       uint32_t b[4];
       ldsm_x4(b, stile + (np * 16 + (m >> 1) * 8 + r) * SROW + kk * 16 + (m & 1) * 8);
       mma_bf16(acc[2 * np], a[kk], b[0], b[1]);
@@ -121,10 +124,11 @@ __device__ __forceinline__ void mma_a_tileT(float (&acc)[8][4], const uint32_t (
 // acc[16 x 64(n)] += P[16 x 64(k)] * T where the tile T is stored [k = 64][n = 64]; P given as the
 // fp32 accumulator fragments of a previous 16 x 64 product, converted to bf16 A fragments
 __device__ __forceinline__ void mma_p_tile(float (&acc)[8][4], const float (&pacc)[8][4],
-                                           const __nv_bfloat16* stile, int lane) {
+                                           const __nv_bfloat16* stile, int lane, int nksteps) {
   const int m = lane >> 3, r = lane & 7;
 #pragma unroll
   for (int kk = 0; kk < 4; ++kk) {
+    if (kk >= nksteps) continue;
     uint32_t a[4];
     a[0] = pack_bf16x2(pacc[2 * kk][0], pacc[2 * kk][1]);
     a[1] = pack_bf16x2(pacc[2 * kk][2], pacc[2 * kk][3]);
@@ -178,6 +182,7 @@ attn_fwd_kernel(const AttnParams p) {
   for (int j = 0; j < 8; ++j) o[j][0] = o[j][1] = o[j][2] = o[j][3] = 0.f;
   float m_run[2] = {-INFINITY, -INFINITY}, l_run[2] = {0.f, 0.f};
   const int qrow[2] = {q0 + warp * 16 + g, q0 + warp * 16 + g + 8};
+  const bool warp_active = (q0 + warp * 16) < p.N;   // strips past the sequence end only help loading
 
   for (int j = 0; j < nkv; ++j) {
     if (j + 1 < nkv) {
@@ -189,10 +194,12 @@ attn_fwd_kernel(const AttnParams p) {
       cp_async_wait<0>();
     }
     __syncthreads();
+    if (warp_active) {
+    const int ngrp = min(4, (p.N - j * TILE + 15) / 16);   // valid 16-row groups of this kv tile
     float sc[8][4];
 #pragma unroll
     for (int n = 0; n < 8; ++n) sc[n][0] = sc[n][1] = sc[n][2] = sc[n][3] = 0.f;
-    mma_a_tileT(sc, qf, sK[j & 1], lane);
+    mma_a_tileT(sc, qf, sK[j & 1], lane, ngrp);
 
     // masking + online softmax (base-2 domain)
     float tmax[2] = {-INFINITY, -INFINITY};
@@ -233,7 +240,8 @@ attn_fwd_kernel(const AttnParams p) {
       o[n][0] *= corr[0], o[n][1] *= corr[0], o[n][2] *= corr[1], o[n][3] *= corr[1];
     }
     l_run[0] += psum[0], l_run[1] += psum[1];
-    mma_p_tile(o, sc, sV[j & 1], lane);
+    mma_p_tile(o, sc, sV[j & 1], lane, ngrp);
+    }
     __syncthreads();
   }
 
@@ -324,6 +332,7 @@ attn_bwd_dq_kernel(const AttnParams p) {
   float dq[8][4];
 #pragma unroll
   for (int j = 0; j < 8; ++j) dq[j][0] = dq[j][1] = dq[j][2] = dq[j][3] = 0.f;
+  const bool warp_active = (q0 + warp * 16) < p.N;
 
   for (int j = 0; j < nkv; ++j) {
     if (j + 1 < nkv) {
@@ -335,14 +344,16 @@ attn_bwd_dq_kernel(const AttnParams p) {
       cp_async_wait<0>();
     }
     __syncthreads();
+    if (warp_active) {
+    const int ngrp = min(4, (p.N - j * TILE + 15) / 16);
     float sc[8][4], dp[8][4];
 #pragma unroll
     for (int n = 0; n < 8; ++n) {
       sc[n][0] = sc[n][1] = sc[n][2] = sc[n][3] = 0.f;
       dp[n][0] = dp[n][1] = dp[n][2] = dp[n][3] = 0.f;
     }
-    mma_a_tileT(sc, qf, sK[j & 1], lane);   // S  = Q K^T
-    mma_a_tileT(dp, dof, sV[j & 1], lane);  // dP = dO V^T
+    mma_a_tileT(sc, qf, sK[j & 1], lane, ngrp);   // S  = Q K^T
+    mma_a_tileT(dp, dof, sV[j & 1], lane, ngrp);  // dP = dO V^T
 #pragma unroll
     for (int n = 0; n < 8; ++n) {
 #pragma unroll
@@ -356,7 +367,8 @@ attn_bwd_dq_kernel(const AttnParams p) {
         sc[n][e] = pv * (dp[n][e] - dlt[r]);  // dS
       }
     }
-    mma_p_tile(dq, sc, sK[j & 1], lane);  // dQ += dS K
+    mma_p_tile(dq, sc, sK[j & 1], lane, ngrp);  // dQ += dS K
+    }
     __syncthreads();
   }
 #pragma unroll
@@ -422,6 +434,7 @@ attn_bwd_dkv_kernel(const AttnParams p) {
     dk[j][0] = dk[j][1] = dk[j][2] = dk[j][3] = 0.f;
     dv[j][0] = dv[j][1] = dv[j][2] = dv[j][3] = 0.f;
   }
+  const bool warp_active = (k0 + warp * 16) < p.N;
 
   for (int j = jq0; j < nq; ++j) {
     const int buf = (j - jq0) & 1;
@@ -433,14 +446,16 @@ attn_bwd_dkv_kernel(const AttnParams p) {
       cp_async_wait<0>();
     }
     __syncthreads();
+    if (warp_active) {
+    const int ngrp = min(4, (p.N - j * TILE + 15) / 16);   // valid 16-row groups of this q tile
     float st[8][4], dpt[8][4];
 #pragma unroll
     for (int n = 0; n < 8; ++n) {
       st[n][0] = st[n][1] = st[n][2] = st[n][3] = 0.f;
       dpt[n][0] = dpt[n][1] = dpt[n][2] = dpt[n][3] = 0.f;
     }
-    mma_a_tileT(st, kf, sQ[buf], lane);    // S^T  = K Q^T
-    mma_a_tileT(dpt, vf, sdO[buf], lane);  // dP^T = V dO^T
+    mma_a_tileT(st, kf, sQ[buf], lane, ngrp);    // S^T  = K Q^T
+    mma_a_tileT(dpt, vf, sdO[buf], lane, ngrp);  // dP^T = V dO^T
     float pt[8][4];
 #pragma unroll
     for (int n = 0; n < 8; ++n) {
@@ -456,8 +471,9 @@ attn_bwd_dkv_kernel(const AttnParams p) {
         st[n][e] = pv * (dpt[n][e] - sDelta[buf][qi]);  // dS^T
       }
     }
-    mma_p_tile(dv, pt, sdO[buf], lane);  // dV += P^T dO
-    mma_p_tile(dk, st, sQ[buf], lane);   // dK += dS^T Q
+    mma_p_tile(dv, pt, sdO[buf], lane, ngrp);  // dV += P^T dO
+    mma_p_tile(dk, st, sQ[buf], lane, ngrp);   // dK += dS^T Q
+    }
     __syncthreads();
   }
 #pragma unroll

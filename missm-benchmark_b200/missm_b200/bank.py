@@ -97,7 +97,8 @@ class LanguageBind(nn.Module):
         if missing_index is not None and self.compaction and len(keys) > 0:
             mi = missing_index.reshape(-1).to(torch.int64).contiguous()
             if not mi.is_cuda:
-                raise RuntimeError("missm_b200: missing_index must be on the CUDA device")
+                raise RuntimeError("missm_b200: missing_index is on the CPU; the B200 path has no CPU fallback "
+                                   "(move the model and its inputs to a CUDA device)")
             codes = [MISSING_TYPE_INDEX.get(k, -1) for k in keys]
             idx, slot, counts = ops.compact_mask(mi, codes)
             counts = counts.tolist()          # the one host sync of the step: sizes of the towers' batches

@@ -68,9 +68,11 @@ def tiny():
     out = {'meta': dict(vision=TINY_V, text=TINY_T, per=TINY_PER, modals=TINY_MODALS, projection_dim=64,
                         B=B, fusion_dim=32, n_classes=3), 'missing_index': missing_index}
     extra = {'depth': 5, 'thermal': 6}
+    names = {}
     for fusion in FUSIONS:
         model = ref_shim.build_reference_model(bank, fusion, modal_types, 3, feature_dims=64, fusion_dim=32,
                                                dropout_prob=0.0, extra_missing_codes=extra)
+        names[fusion] = {k: tuple(v.shape) for k, v in model.state_dict().items()}
         load_synth(model)
         model.eval()
         with torch.no_grad():
@@ -129,6 +131,8 @@ def tiny():
     amodel.resize_pos(emb_mod, acfg.vision_config)
     out['resize_pos/in'] = table
     out['resize_pos/out'] = emb_mod.position_embedding.weight.detach().clone()
+    torch.save({'meta': dict(vision=TINY_V, text=TINY_T, per=TINY_PER, modals=TINY_MODALS), 'fusions': names},
+               os.path.join(GOLD, 'reference_param_shapes.pt'))
     torch.save(out, os.path.join(GOLD, 'tiny_bank.pt'))
     print('tiny golden written:', {k: (tuple(v.shape) if torch.is_tensor(v) else type(v).__name__)
                                   for k, v in out.items() if not k.startswith('grad/')})

@@ -1,0 +1,126 @@
+"""CPU-only tests of the host side: the drop-in module tree carries the reference's parameter
+names and shapes, configs mirror the reference defaults, the product refuses to run on the CPU
+(no fallback), and the benchmark's synthetic problem follows the reference's generators."""
+import os
+import sys
+import types
+
+import pytest
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.join(os.path.dirname(HERE), "oracle"))
+import restatement as R  # noqa: E402
+
+GOLD = os.path.join(HERE, "golden")
+
+
+def test_dropin_import_surface():
+    import languagebind as lb
+    from src.model.baseline import finetune_model, missing_type_index  # noqa: F401
+    for name in ("LanguageBind", "to_device", "transform_dict", "LanguageBindImageTokenizer", "model_dict",
+                 "config_dict"):
+        assert hasattr(lb, name), name
+    assert set(lb.model_dict) == {'thermal', 'image', 'video', 'depth', 'audio'} == set(lb.transform_dict)
+    assert {k: missing_type_index[k] for k in ('language', 'video', 'audio', 'image')} == \
+        {'language': 1, 'video': 2, 'audio': 3, 'image': 4}           # src/model/baseline.py:8 unchanged
+
+
+def test_parameter_names_and_shapes_match_reference():
+    """tests/golden/reference_param_shapes.pt holds state-dict names/shapes of the UNMODIFIED
+    reference modules (oracle/make_golden.py); the product's module tree must be identical."""
+    path = os.path.join(GOLD, "reference_param_shapes.pt")
+    if not os.path.exists(path):
+        pytest.skip("name list not generated")
+    from missm_b200 import shapes
+    ref = torch.load(path, weights_only=False)
+    meta = ref['meta']
+    cfgs = {}
+    for m in meta['modals']:
+        d = {k: v for k, v in meta['vision'].items() if k != 'lora_r'}
+        d.update(meta['per'].get(m, {}))
+        cfgs[m] = R.vision_config(**d)
+    tcfg = R.text_config(**meta['text'])
+    for fusion, names in ref['fusions'].items():
+        mine = dict(shapes.reference_named_shapes(cfgs, tcfg, ['language'] + meta['modals'], fusion,
+                                                  projection_dim=64, fusion_dim=32))
+        theirs = {k: tuple(v) for k, v in names.items() if not k.endswith('position_ids')}
+        mine = {k: v for k, v in mine.items() if not k.endswith('position_ids')}
+        assert set(mine) == set(theirs), (fusion, sorted(set(mine) ^ set(theirs))[:8])
+        for k in theirs:
+            assert mine[k] == theirs[k], (fusion, k, mine[k], theirs[k])
+
+
+def test_config_defaults_mirror_reference():
+    from missm_b200 import config as C
+    v, t = C.CLIPVisionConfig(), C.CLIPTextConfig()
+    assert (v.hidden_size, v.intermediate_size, v.num_hidden_layers, v.patch_size, v.hidden_act, v.lora_r,
+            v.layer_norm_eps, v.add_time_attn, v.num_frames) == (768, 3072, 12, 32, "quick_gelu", 2, 1e-5, False, 1)
+    assert (t.vocab_size, t.hidden_size, t.max_position_embeddings, t.eos_token_id) == (49408, 512, 77, 49407)
+    c = C.LanguageBindAudioConfig(vision_config=dict(num_mel_bins=112, target_length=1036, patch_size=14))
+    assert c.logit_scale_init_value == 2.6592 and c.vision_config.target_length == 1036
+    with pytest.raises(ValueError):
+        from missm_b200 import towers
+        towers.LanguageBindImage(types.SimpleNamespace(text_config={}, vision_config={}, projection_dim=8,
+                                                       logit_scale_init_value=1.0, initializer_factor=1.0))
+
+
+def test_audio_grid_and_position_table_shapes():
+    from missm_b200 import towers, config as C
+    with torch.device('meta'):
+        m = towers.LanguageBindAudio(towers.LanguageBindAudio.synthetic_config())
+    assert m.vision_model.embeddings.position_embedding.weight.shape == (593, 1024)   # 8 x 74 + 1
+    table = R.synth_param('t', (17, 128), 0.5)
+    assert torch.allclose(towers.resize_pos_table(table, [2, 5]), R.resize_pos(table, [2, 5]))
+
+
+def test_product_has_no_cpu_fallback():
+    from missm_b200 import shapes
+    v = dict(hidden_size=128, intermediate_size=128, num_hidden_layers=1, num_attention_heads=2, patch_size=14,
+             image_size=28)
+    t = dict(hidden_size=128, intermediate_size=128, num_hidden_layers=1, num_attention_heads=2, vocab_size=64)
+    model = shapes.build_finetune({'image': v}, t, ['image'], 'sum', 3, 64, 32)
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        model({'image': {'pixel_values': torch.randn(2, 3, 28, 28)}}, torch.zeros(2, dtype=torch.long))
+
+
+def test_out_of_scope_heads_are_refused():
+    from src.model.baseline import finetune_model
+    args = types.SimpleNamespace(fusion_type='graph_fusion', modality_types=['image'], feature_dims=8, fusion_dim=8,
+                                 dropout_prob=0.0)
+    with pytest.raises(NotImplementedError):
+        finetune_model(args, 3, torch.nn.Identity())
+
+
+def test_return_arity_per_fusion_type():
+    """train_ddp.py:232-249 unpacks tuples for the distillation heads."""
+    from src.model import baseline as B
+    args = types.SimpleNamespace(modality_types=['a', 'b'], feature_dims=8, fusion_dim=8, dropout_prob=0.0)
+    B.missing_type_index.update({'a': 11, 'b': 12})
+    try:
+        batch = {'a': torch.randn(3, 8), 'b': torch.randn(3, 8)}
+        mi = torch.tensor([0, 11, 12])
+        d = B.modal_distillation(args, 3)
+        feats, logits = d(batch, mi)
+        assert feats.shape == (3, 16) and logits.shape == (3, 3) and feats[1, :8].abs().sum() == 0
+        s = B.modal_self_distillation(args, 3).train()
+        masks, stu, tea, logits = s(batch, mi)
+        assert len(masks) == 2 and len(stu) == 2 and tea.shape == (3, 8) and logits.shape == (3, 3)
+        assert s.eval()(batch, mi).shape == (3, 3)
+        c = B.modal_concat(args, 3)
+        c.set_statistics({'a': [1.0] * 8, 'b': [2.0] * 8}, ['a', 'b'])
+        assert c.statistics_a.tolist() == [1.0] * 8 and c(batch, mi).shape == (3, 3)
+    finally:
+        B.missing_type_index.pop('a'), B.missing_type_index.pop('b')
+
+
+def test_synthetic_inputs_follow_the_loader_contract():
+    cfgs = {'video': R.vision_config(patch_size=14, image_size=28, add_time_attn=True, num_frames=8),
+            'audio': R.vision_config(patch_size=14, num_mel_bins=112, target_length=1036)}
+    t = R.text_config()
+    d = R.synth_inputs(['language', 'video', 'audio'], 3, cfgs, t)
+    assert d['video']['pixel_values'].shape == (3, 3, 8, 28, 28)           # b c t h w
+    assert d['audio']['pixel_values'].shape == (3, 3, 112, 1036)
+    ids, am = d['language']['input_ids'], d['language']['attention_mask']
+    assert ids.shape == (3, 77) and ids.dtype == torch.int64 and am[:, :21].all() and not am[:, 21:].any()
+    assert (ids.argmax(-1) == 20).all()                                     # first EOT
