@@ -17,6 +17,8 @@
 // addressed through (seq_outer, seq_inner, tok_stride) so the temporal attention of the video
 // tower reads the [(b t) n d] activations in place -- the einops rearranges of
 // modeling_image.py:112-118,127 are never materialised.
+#include <cstdlib>
+
 #include "../../include/missm_b200.h"
 #include "missm_common.cuh"
 
@@ -514,8 +516,19 @@ static int fill_params(AttnParams& p, const missm_attn_args* a) {
 
 using namespace missm;
 
+namespace missm {
+int attention_fwd_tc(const missm_attn_args* a, cudaStream_t stream);  // attention_tc.cu
+}
+
 extern "C" int missm_attention_fwd(const missm_attn_args* a, void* stream) {
   if (a->n_seq == 0) return 0;
+  // tcgen05 path for the shapes it covers (spatial ViT attention); general shapes below
+  static const bool legacy_only = getenv("MISSM_ATTN_LEGACY") != nullptr;
+  if (!legacy_only) {
+    MISSM_REQUIRE(a->qkv && a->out, "attention_fwd: null tensor");
+    const int rc = attention_fwd_tc(a, static_cast<cudaStream_t>(stream));
+    if (rc >= 0) return rc;
+  }
   AttnParams p;
   if (int rc = fill_params(p, a)) return rc;
   MISSM_REQUIRE(p.qkv && p.out, "attention_fwd: null tensor");

@@ -381,6 +381,24 @@ int make_tmap_2d_bf16(CUtensorMap* out, const void* base, uint64_t inner, uint64
   return 0;
 }
 
+// 3-D bf16 tensor (d0 contiguous; d1, d2 with element strides), box = b0 x b1 x 1, 128B swizzle
+int make_tmap_3d_bf16(CUtensorMap* out, const void* base, uint64_t d0, uint64_t d1, uint64_t d2,
+                      uint64_t stride1_elems, uint64_t stride2_elems, uint32_t b0, uint32_t b1) {
+  EncodeTiledFn fn = get_encode_fn();
+  MISSM_REQUIRE(fn != nullptr, "cuTensorMapEncodeTiled entry point unavailable");
+  MISSM_REQUIRE((reinterpret_cast<uintptr_t>(base) & 15) == 0, "TMA base not 16B aligned");
+  MISSM_REQUIRE((stride1_elems * 2) % 16 == 0 && (stride2_elems * 2) % 16 == 0, "TMA strides not 16 B multiples");
+  cuuint64_t gdim[3] = {d0, d1, d2};
+  cuuint64_t gstride[2] = {stride1_elems * 2, stride2_elems * 2};
+  cuuint32_t box[3] = {b0, b1, 1};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(base), gdim, gstride, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  MISSM_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled(3d) failed with %d", (int)r);
+  return 0;
+}
+
 template <int BN, int EPI, bool OUT_F32>
 static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmParams& p,
                        int grid, cudaStream_t stream) {
