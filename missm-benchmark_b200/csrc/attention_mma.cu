@@ -518,6 +518,7 @@ using namespace missm;
 
 namespace missm {
 int attention_fwd_tc(const missm_attn_args* a, cudaStream_t stream);  // attention_tc.cu
+int attention_bwd_tc(const missm_attn_args* a, cudaStream_t stream);  // attention_tc_bwd.cu
 }
 
 extern "C" int missm_attention_fwd(const missm_attn_args* a, void* stream) {
@@ -548,6 +549,11 @@ extern "C" int missm_attention_bwd(const missm_attn_args* a, void* stream) {
   int dgrid = static_cast<int>((total + 255) / 256);
   if (dgrid > 16 * kNumSMs) dgrid = 16 * kNumSMs;
   attn_delta_kernel<<<dgrid, 256, 0, st>>>(p);
+  static const bool legacy_only = getenv("MISSM_ATTN_LEGACY") != nullptr;
+  if (!legacy_only) {
+    const int rc = attention_bwd_tc(a, st);   // tcgen05 path for the shapes it covers
+    if (rc >= 0) return rc;
+  }
   dim3 grid((p.N + TILE - 1) / TILE, p.H, p.n_seq);
   attn_bwd_dkv_kernel<<<grid, kAttnThreads, 0, st>>>(p);
   attn_bwd_dq_kernel<<<grid, kAttnThreads, 0, st>>>(p);

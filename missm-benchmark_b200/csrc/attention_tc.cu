@@ -43,12 +43,6 @@ struct AttnTcSmem {
   uint32_t tmem_base;
 };
 
-__device__ __forceinline__ void tmem_st_32x32b_x8(uint32_t taddr, const uint32_t (&r)[8]) {
-  asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"r"(taddr),
-               "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7])
-               : "memory");
-}
-
 __global__ void __launch_bounds__(kTcThreads, 1)
 attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, const AttnTcParams p) {
   extern __shared__ uint8_t smem_raw[];
@@ -246,9 +240,6 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, const AttnTcParam
     tmem_dealloc(tmem, 512);
   }
 }
-
-int make_tmap_3d_bf16(CUtensorMap* out, const void* base, uint64_t d0, uint64_t d1, uint64_t d2,
-                      uint64_t stride1_elems, uint64_t stride2_elems, uint32_t b0, uint32_t b1);
 
 // returns 0 if launched, -1 if the shape is not handled by this kernel (caller falls back to the
 // general mma.sync path), > 0 on error

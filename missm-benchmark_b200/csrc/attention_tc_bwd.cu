@@ -1,0 +1,540 @@
+// Fused attention BACKWARD on the 5th-gen tensor cores (tcgen05 / TMEM / TMA), head_dim 64,
+// non-causal, unmasked, N <= 272 tokens: the ViT-L/14 spatial attention of the image / depth /
+// thermal / video towers (N = 257) -- the autograd twin of transformers 4.3x CLIPAttention's
+// bmm -> softmax -> bmm chain called at languagebind/image/modeling_image.py:140.
+//
+// Two kernels from one template, neither of which ever puts a score in shared memory or HBM:
+//   DKV (row index = key):    S^T = K Q^T, dP^T = V dO^T       (tcgen05.mma, smem x smem -> TMEM)
+//                             P^T = exp2(S^T log2e - lse), dS^T = P^T o (dP^T - delta)
+//                               -> bf16, written back IN PLACE in TMEM (tcgen05.ld / tcgen05.st)
+//                             dV += P^T dO,  dK += dS^T Q      (tcgen05.mma, A operand from TMEM)
+//   DQ  (row index = query):  S = Q K^T, dP = dO V^T;  dS likewise;  dQ += dS K
+// One persistent CTA per SM walks (sequence, head) items.  The "column side" operands of an item
+// (DKV: all of Q and dO; DQ: all of K and V; 272 rows x 64, 34 KB each) are TMA-loaded once into
+// 128B-swizzled shared memory, double-buffered across items; the 128-row "row side" tiles are
+// double-buffered across tiles.  Columns are processed in chunks of <= 96: the two fp32 score
+// chunks (2 x 96 TMEM columns) are double-buffered, two softmax warpgroups ping-pong over the chunks
+// (one thread per row, 32-column register blocks), and the MMA warp issues the score MMAs of chunk
+// n+1 before the accumulation MMAs of chunk n, so tensor pipe, MUFU and TMEM traffic overlap.
+// The same shared-memory tile serves as K-major operand of the score MMAs and as MN-major operand of
+// the accumulation MMAs -- no transposed copy of anything exists.
+//
+// TMEM columns: [0,96) S_0  [96,192) dP_0  [192,288) S_1  [288,384) dP_1  [384,512) accumulators.
+// Bound: MUFU (one ex2 per score and kernel) / tensor.  Algorithmic work per item: DKV 8, DQ 6
+// (together the usual "2.5 x forward" counts 10) x N^2 x 64 flop.
+#include <cstdlib>
+
+#include "../../include/missm_b200.h"
+#include "missm_common.cuh"
+
+namespace missm {
+
+constexpr int BW_THREADS = 384;      // warp 0 TMA, 1 MMA, 2 TMEM alloc, 3 column statistics, 4-7 / 8-11 softmax WGs
+constexpr int BW_CW = 96;            // score chunk width (columns)
+constexpr int BW_MAXN = 272;         // resident rows (multiple of 16)
+constexpr int BW_RES_BYTES = BW_MAXN * 128;   // one resident operand (rows of 64 bf16)
+constexpr int BW_TILE_BYTES = 128 * 128;      // one row-side tile
+constexpr int BW_STAT = 288;         // floats per column-statistics array
+constexpr int BW_ACC_COL = 384;
+constexpr float kLog2eBw = 1.4426950408889634f;
+
+struct AttnBwdTcParams {
+  int N, H, D, n_items;
+  int sw;      // N rounded up to 16
+  int nt;      // row tiles (128 rows)
+  int nc;      // column chunks
+  const float* lse;    // [n_seq, H, N]
+  const float* delta;  // [n_seq, H, N]
+  __nv_bfloat16* dqkv;
+  long ld_qkv;
+  float q_scale;
+  long long* trace;    // debugging only (MISSM_ATTN_TRACE): [4096] x (tag, step, clock) of CTA 0
+};
+
+__device__ __forceinline__ void bw_trace(const AttnBwdTcParams& p, int slot_base, uint32_t& cnt, int tag, uint32_t n) {
+  if (p.trace != nullptr && blockIdx.x == 0 && cnt < 330) {
+    long long* t = p.trace + (slot_base * 330 + cnt) * 3;
+    t[0] = tag, t[1] = n, t[2] = clock64();
+    ++cnt;
+  }
+}
+
+struct AttnBwdSmem {
+  uint64_t res_full[2], res_empty[2];
+  uint64_t a_full[2], a_empty[2];
+  uint64_t s_full[2], p_full[2], sbuf_empty[2];
+  uint64_t acc_full[2], acc_empty[2];
+  uint64_t stat_full[2], stat_empty[2];
+  uint32_t tmem_base;
+};
+
+// position in the flattened (item, row tile, column chunk) sequence of this CTA
+struct BwCursor {
+  int item, tile, chunk;
+  uint32_t n, tcount, it;
+  __device__ __forceinline__ void init() { item = blockIdx.x, tile = chunk = 0, n = tcount = it = 0; }
+  __device__ __forceinline__ void advance(const AttnBwdTcParams& p) {
+    ++n;
+    if (++chunk == p.nc) {
+      chunk = 0, ++tcount;
+      if (++tile == p.nt) tile = 0, item += gridDim.x, ++it;
+    }
+  }
+  __device__ __forceinline__ bool valid(const AttnBwdTcParams& p) const { return item < p.n_items; }
+};
+
+__device__ __forceinline__ float4 lds_f4(uint32_t saddr) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(saddr));
+  return v;
+}
+
+// One row x `wc` score columns (wc % 16 == 0, <= 96):  dS (and P) -> packed bf16, written back in
+// place.  16-column register blocks, double-buffered: the TMEM loads of block b+1 are in flight while
+// block b is computed (tcgen05.wait::ld only covers loads issued before it).
+// DKV: per-COLUMN statistics from shared memory (stat_saddr -> -lse*log2e of column c0; delta
+// BW_STAT floats further);  DQ: per-row statistics in registers.
+template <bool DKV>
+__device__ __forceinline__ void bwd_chunk(uint32_t t_s, uint32_t t_dp, uint32_t stat_saddr, float nl_row,
+                                          float de_row, int c0, int wc, int N) {
+  uint32_t s[2][16], dp[2][16];
+  tmem_ld_32x32b_x16(t_s, s[0]);
+  tmem_ld_32x32b_x16(t_dp, dp[0]);
+  const int nb = wc >> 4;
+#pragma unroll
+  for (int b = 0; b < BW_CW / 16; ++b) {
+    if (b < nb) {   // warp-uniform
+      tmem_ld_wait();
+      if (b + 1 < nb) {
+        tmem_ld_32x32b_x16(t_s + (b + 1) * 16, s[(b + 1) & 1]);
+        tmem_ld_32x32b_x16(t_dp + (b + 1) * 16, dp[(b + 1) & 1]);
+      }
+      uint32_t pp[8], dd[8];
+#pragma unroll
+      for (int j = 0; j < 16; j += 4) {
+        float nl[4], de[4];
+        if constexpr (DKV) {
+          const float4 x = lds_f4(stat_saddr + (b * 16 + j) * 4);                  // broadcast reads
+          const float4 y = lds_f4(stat_saddr + (BW_STAT + b * 16 + j) * 4);
+          nl[0] = x.x, nl[1] = x.y, nl[2] = x.z, nl[3] = x.w;
+          de[0] = y.x, de[1] = y.y, de[2] = y.z, de[3] = y.w;
+        } else {
+          nl[0] = nl[1] = nl[2] = nl[3] = nl_row;
+          de[0] = de[1] = de[2] = de[3] = de_row;
+        }
+        float pv[4], dv[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          pv[e] = fast_ex2(fmaf(__uint_as_float(s[b & 1][j + e]), kLog2eBw, nl[e]));
+          dv[e] = pv[e] * (__uint_as_float(dp[b & 1][j + e]) - de[e]);
+        }
+        if constexpr (!DKV) {
+          // key columns past N hold zero-filled K rows; keep 0 * inf out of the dQ accumulation
+          if (c0 + b * 16 + 16 > N) {
+#pragma unroll
+            for (int e = 0; e < 4; ++e)
+              if (c0 + b * 16 + j + e >= N) dv[e] = 0.f;
+          }
+        }
+        pp[j >> 1] = pack_bf16x2(pv[0], pv[1]), pp[(j >> 1) + 1] = pack_bf16x2(pv[2], pv[3]);
+        dd[j >> 1] = pack_bf16x2(dv[0], dv[1]), dd[(j >> 1) + 1] = pack_bf16x2(dv[2], dv[3]);
+      }
+      if constexpr (DKV) tmem_st_32x32b_x8(t_s + b * 8, pp);
+      tmem_st_32x32b_x8(t_dp + b * 8, dd);
+    }
+  }
+}
+
+__device__ __forceinline__ void store_row64_bf16(__nv_bfloat16* dst, const uint32_t (&a)[32],
+                                                 const uint32_t (&b)[32], float scale) {
+  uint4* d4 = reinterpret_cast<uint4*>(dst);
+#pragma unroll
+  for (int j = 0; j < 32; j += 8) {
+    uint4 v;
+    v.x = pack_bf16x2(__uint_as_float(a[j]) * scale, __uint_as_float(a[j + 1]) * scale);
+    v.y = pack_bf16x2(__uint_as_float(a[j + 2]) * scale, __uint_as_float(a[j + 3]) * scale);
+    v.z = pack_bf16x2(__uint_as_float(a[j + 4]) * scale, __uint_as_float(a[j + 5]) * scale);
+    v.w = pack_bf16x2(__uint_as_float(a[j + 6]) * scale, __uint_as_float(a[j + 7]) * scale);
+    d4[j >> 3] = v;
+  }
+#pragma unroll
+  for (int j = 0; j < 32; j += 8) {
+    uint4 v;
+    v.x = pack_bf16x2(__uint_as_float(b[j]) * scale, __uint_as_float(b[j + 1]) * scale);
+    v.y = pack_bf16x2(__uint_as_float(b[j + 2]) * scale, __uint_as_float(b[j + 3]) * scale);
+    v.z = pack_bf16x2(__uint_as_float(b[j + 4]) * scale, __uint_as_float(b[j + 5]) * scale);
+    v.w = pack_bf16x2(__uint_as_float(b[j + 6]) * scale, __uint_as_float(b[j + 7]) * scale);
+    d4[4 + (j >> 3)] = v;
+  }
+}
+
+// tm128 / tm16: [3D cols, N rows, n_seq] views of qkv with 64 x 128 and 64 x 16 boxes; td128 / td16:
+// the same for d_out (D cols).
+template <bool DKV>
+__global__ void __launch_bounds__(BW_THREADS, 1)
+attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm128, const __grid_constant__ CUtensorMap tm16,
+                   const __grid_constant__ CUtensorMap td128, const __grid_constant__ CUtensorMap td16,
+                   const AttnBwdTcParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
+  // resident column-side operands: [item buffer][operand]
+  uint8_t* sRes = smem;                                   // 2 x 2 x 34 KB
+  uint8_t* sTile = sRes + 4 * BW_RES_BYTES;               // [tile buffer][operand]: 2 x 2 x 16 KB
+  float* sStat = reinterpret_cast<float*>(sTile + 4 * BW_TILE_BYTES);   // [item buffer][nlse2 | delta][BW_STAT]
+  AttnBwdSmem* sh = reinterpret_cast<AttnBwdSmem*>(sStat + 4 * BW_STAT);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  constexpr int NACC = DKV ? 1 : 2;   // DKV: dV | dK fill the 128 accumulator columns; DQ: dQ double-buffered
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tm128), tma_prefetch_desc(&tm16), tma_prefetch_desc(&td128), tma_prefetch_desc(&td16);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&sh->res_full[i], 1), mbar_init(&sh->res_empty[i], 1);
+      mbar_init(&sh->a_full[i], 1), mbar_init(&sh->a_empty[i], 1);
+      mbar_init(&sh->s_full[i], 1), mbar_init(&sh->p_full[i], 128), mbar_init(&sh->sbuf_empty[i], 1);
+      mbar_init(&sh->acc_full[i], 1), mbar_init(&sh->acc_empty[i], 128);
+      mbar_init(&sh->stat_full[i], 32), mbar_init(&sh->stat_empty[i], 256);
+    }
+    fence_mbar_init();
+  }
+  if (warp == 2) {
+    tmem_alloc(&sh->tmem_base, 512);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = sh->tmem_base;
+
+  const int n_full = p.sw / 128;             // full 128-row boxes of a resident operand
+  const int n_rem16 = (p.sw % 128) / 16;     // remaining 16-row boxes
+  // column offsets (elements) of the operands inside a qkv row
+  const int col_q = 0, col_k = p.D, col_v = 2 * p.D;
+
+  if (warp == 0) {
+    // ================================ TMA producer ====================================
+    // (converged warp waits; one elected lane arms the barrier and issues the copies)
+    {
+      uint32_t it = 0, tcount = 0;
+      const uint32_t res_tx = 2u * static_cast<uint32_t>(n_full * BW_TILE_BYTES + n_rem16 * 16 * 128);
+      for (int item = blockIdx.x; item < p.n_items; item += gridDim.x, ++it) {
+        const int s = item / p.H, h = item % p.H;
+        const int rb = it & 1;
+        mbar_wait(&sh->res_empty[rb], ((it >> 1) & 1) ^ 1);
+        if (elect_one_sync()) {
+          mbar_arrive_expect_tx(&sh->res_full[rb], res_tx);
+          uint8_t* r0 = sRes + (rb * 2 + 0) * BW_RES_BYTES;
+          uint8_t* r1 = sRes + (rb * 2 + 1) * BW_RES_BYTES;
+          // DKV: resident = Q, dO.   DQ: resident = K, V.
+          for (int j = 0; j < n_full; ++j) {
+            tma_load_3d(r0 + j * BW_TILE_BYTES, &tm128, &sh->res_full[rb], (DKV ? col_q : col_k) + h * 64, j * 128, s);
+            if (DKV) tma_load_3d(r1 + j * BW_TILE_BYTES, &td128, &sh->res_full[rb], h * 64, j * 128, s);
+            else     tma_load_3d(r1 + j * BW_TILE_BYTES, &tm128, &sh->res_full[rb], col_v + h * 64, j * 128, s);
+          }
+          for (int j = 0; j < n_rem16; ++j) {
+            const int row = n_full * 128 + j * 16;
+            tma_load_3d(r0 + row * 128, &tm16, &sh->res_full[rb], (DKV ? col_q : col_k) + h * 64, row, s);
+            if (DKV) tma_load_3d(r1 + row * 128, &td16, &sh->res_full[rb], h * 64, row, s);
+            else     tma_load_3d(r1 + row * 128, &tm16, &sh->res_full[rb], col_v + h * 64, row, s);
+          }
+        }
+        __syncwarp();
+        for (int t = 0; t < p.nt; ++t, ++tcount) {
+          const int ab = tcount & 1;
+          mbar_wait(&sh->a_empty[ab], ((tcount >> 1) & 1) ^ 1);
+          if (elect_one_sync()) {
+            mbar_arrive_expect_tx(&sh->a_full[ab], 2 * BW_TILE_BYTES);
+            uint8_t* a0 = sTile + (ab * 2 + 0) * BW_TILE_BYTES;
+            uint8_t* a1 = sTile + (ab * 2 + 1) * BW_TILE_BYTES;
+            // DKV: tiles = K, V.   DQ: tiles = Q, dO.
+            tma_load_3d(a0, &tm128, &sh->a_full[ab], (DKV ? col_k : col_q) + h * 64, t * 128, s);
+            if (DKV) tma_load_3d(a1, &tm128, &sh->a_full[ab], col_v + h * 64, t * 128, s);
+            else     tma_load_3d(a1, &td128, &sh->a_full[ab], h * 64, t * 128, s);
+          }
+          __syncwarp();
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ================================ MMA issuer ======================================
+    // the whole (converged) warp walks the schedule and waits; one elected lane issues
+    {
+      const uint32_t idesc_acc = umma_idesc_bf16_f32(128, 64, 0, 1);   // A from TMEM, B MN-major
+      // K-major (score MMAs) and MN-major (accumulation MMAs) views of a tile share one encoding
+      const uint64_t desc_tile = umma_smem_desc_sw128(smem_u32(sTile), 16, 1024);
+      const uint64_t desc_res = umma_smem_desc_sw128(smem_u32(sRes), 16, 1024);
+      uint32_t tr = 0;
+      auto issue_scores = [&](const BwCursor& c) {
+        const int rb = c.it & 1, ab = c.tcount & 1, sb = c.n & 1;
+        if (c.chunk == 0) {
+          if (c.tile == 0) mbar_wait(&sh->res_full[rb], (c.it >> 1) & 1);
+          mbar_wait(&sh->a_full[ab], (c.tcount >> 1) & 1);
+        }
+        mbar_wait(&sh->sbuf_empty[sb], ((c.n >> 1) & 1) ^ 1);
+        tc_fence_after();
+        if (lane == 0) bw_trace(p, 0, tr, 1, c.n);
+        const int c0 = c.chunk * BW_CW;
+        const int wc = min(BW_CW, p.sw - c0);
+        const uint32_t idesc = umma_idesc_bf16_f32(128, wc, 0, 0);
+        // descriptors differ only in the 16-byte-granular start address: base + (byte offset >> 4)
+        const uint64_t a0 = desc_tile + ((ab * 2 + 0) * (BW_TILE_BYTES >> 4));
+        const uint64_t a1 = desc_tile + ((ab * 2 + 1) * (BW_TILE_BYTES >> 4));
+        const uint64_t b0 = desc_res + ((rb * 2 + 0) * (BW_RES_BYTES >> 4) + c0 * 8);
+        const uint64_t b1 = desc_res + ((rb * 2 + 1) * (BW_RES_BYTES >> 4) + c0 * 8);
+        const uint32_t d_s = tmem + sb * 192, d_dp = d_s + 96;
+        if (elect_one_sync()) {
+          // the two accumulation chains are interleaved: back-to-back MMAs into the SAME TMEM
+          // accumulator serialise on its read-modify-write latency (~100 cycles measured for these
+          // small shapes), independent chains overlap
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            umma_f16_ss(d_s, a0 + k * 2, b0 + k * 2, idesc, k > 0);
+            umma_f16_ss(d_dp, a1 + k * 2, b1 + k * 2, idesc, k > 0);
+          }
+          umma_commit(&sh->s_full[sb]);
+        }
+        __syncwarp();
+        if (lane == 0) bw_trace(p, 0, tr, 2, c.n);
+      };
+      auto issue_accum = [&](const BwCursor& c) {
+        const int rb = c.it & 1, ab = c.tcount & 1, sb = c.n & 1;
+        const int acc = DKV ? 0 : (c.tcount & 1);
+        const uint32_t acc_use = DKV ? c.tcount : (c.tcount >> 1);
+        mbar_wait(&sh->p_full[sb], (c.n >> 1) & 1);
+        if (lane == 0) bw_trace(p, 0, tr, 3, c.n);
+        if (c.chunk == 0) mbar_wait(&sh->acc_empty[acc], (acc_use & 1) ^ 1);
+        tc_fence_after();
+        if (lane == 0) bw_trace(p, 0, tr, 4, c.n);
+        const int c0 = c.chunk * BW_CW;
+        const int ksteps = min(BW_CW, p.sw - c0) / 16;
+        const uint64_t b0 = desc_res + ((rb * 2 + 0) * (BW_RES_BYTES >> 4) + c0 * 8);
+        const uint64_t b1 = desc_res + ((rb * 2 + 1) * (BW_RES_BYTES >> 4) + c0 * 8);
+        const uint32_t t_p = tmem + sb * 192, t_ds = t_p + 96;
+        if (elect_one_sync()) {
+          if constexpr (DKV) {
+            const uint32_t d_dv = tmem + BW_ACC_COL, d_dk = d_dv + 64;
+#pragma unroll
+            for (int k = 0; k < BW_CW / 16; ++k) {
+              if (k < ksteps) {
+                umma_f16_ts(d_dv, t_p + k * 8, b1 + k * 128, idesc_acc, (c.chunk | k) != 0);    // dV += P^T dO
+                umma_f16_ts(d_dk, t_ds + k * 8, b0 + k * 128, idesc_acc, (c.chunk | k) != 0);   // dK += dS^T Q
+              }
+            }
+          } else {
+            const uint32_t d_dq = tmem + BW_ACC_COL + acc * 64;
+#pragma unroll
+            for (int k = 0; k < BW_CW / 16; ++k)     // dQ += dS K
+              if (k < ksteps) umma_f16_ts(d_dq, t_ds + k * 8, b0 + k * 128, idesc_acc, (c.chunk | k) != 0);
+          }
+          umma_commit(&sh->sbuf_empty[sb]);
+          if (c.chunk == p.nc - 1) {
+            umma_commit(&sh->acc_full[acc]);
+            umma_commit(&sh->a_empty[ab]);
+            if (c.tile == p.nt - 1) umma_commit(&sh->res_empty[rb]);
+          }
+        }
+        __syncwarp();
+        if (lane == 0) bw_trace(p, 0, tr, 5, c.n);
+      };
+      BwCursor cs, cp;
+      cs.init(), cp.init();
+      if (cs.valid(p)) {
+        issue_scores(cs);
+        cs.advance(p);
+      }
+      while (cp.valid(p)) {
+        if (cs.valid(p)) {
+          issue_scores(cs);
+          cs.advance(p);
+        }
+        issue_accum(cp);
+        cp.advance(p);
+      }
+    }
+  } else if (warp == 3) {
+    // ===================== column statistics (DKV): -lse*log2e and delta per query ===========
+    if constexpr (DKV) {
+      uint32_t it = 0;
+      for (int item = blockIdx.x; item < p.n_items; item += gridDim.x, ++it) {
+        const int sbuf = it & 1;
+        mbar_wait(&sh->stat_empty[sbuf], ((it >> 1) & 1) ^ 1);
+        float* nl = sStat + (sbuf * 2 + 0) * BW_STAT;
+        float* de = sStat + (sbuf * 2 + 1) * BW_STAT;
+        const long base = static_cast<long>(item) * p.N;     // item = s * H + h
+        for (int q = lane; q < BW_STAT; q += 32) {
+          const bool ok = q < p.N;
+          nl[q] = ok ? -p.lse[base + q] * kLog2eBw : -INFINITY;
+          de[q] = ok ? p.delta[base + q] : 0.f;
+        }
+        mbar_arrive(&sh->stat_full[sbuf]);
+      }
+    }
+  } else if (warp >= 4) {
+    // ========================= softmax warpgroups (one thread per row) =================
+    const int g = (warp - 4) >> 2;       // warpgroup: takes the steps with n % 2 == g
+    const int q = warp & 3;              // TMEM lane quarter
+    const uint32_t lane_addr = static_cast<uint32_t>(q * 32) << 16;
+    float nl_row = 0.f, de_row = 0.f, nl_pre = 0.f, de_pre = 0.f;
+    int stats_tile = -1, pre_tile = -1;
+    uint32_t tr = 0;
+    const bool tracer = (q == 0 && lane == 0);
+    BwCursor c;
+    c.init();
+    while (c.valid(p)) {
+      const uint32_t it_now = c.it;
+      if ((c.n & 1) == static_cast<uint32_t>(g)) {
+        const int row = c.tile * 128 + q * 32 + lane;
+        const bool warp_has_rows = c.tile * 128 + q * 32 < p.N;
+        uint32_t stat_saddr = 0;
+        if constexpr (DKV) {
+          mbar_wait(&sh->stat_full[c.it & 1], (c.it >> 1) & 1);   // returns at once after the first pass
+          stat_saddr = smem_u32(sStat + (c.it & 1) * 2 * BW_STAT);
+        } else {
+          if (stats_tile != static_cast<int>(c.tcount)) {
+            // this tile's row statistics were requested one tile ago; request the next tile's now
+            stats_tile = static_cast<int>(c.tcount);
+            if (pre_tile == stats_tile) {
+              nl_row = nl_pre, de_row = de_pre;
+            } else {
+              const bool ok = row < p.N;
+              const long li = static_cast<long>(c.item) * p.N + (ok ? row : 0);
+              nl_row = ok ? p.lse[li] : INFINITY;
+              de_row = ok ? p.delta[li] : 0.f;
+            }
+            nl_row *= -kLog2eBw;
+            const int nx_tile = (c.tile + 1 < p.nt) ? c.tile + 1 : 0;
+            const int nx_item = (c.tile + 1 < p.nt) ? c.item : c.item + static_cast<int>(gridDim.x);
+            pre_tile = stats_tile + 1;
+            const int nx_row = nx_tile * 128 + q * 32 + lane;
+            const bool ok = nx_row < p.N && nx_item < p.n_items;
+            const long li = ok ? static_cast<long>(nx_item) * p.N + nx_row : 0;
+            nl_pre = ok ? p.lse[li] : INFINITY;
+            de_pre = ok ? p.delta[li] : 0.f;
+          }
+        }
+        if (tracer) bw_trace(p, 1 + g, tr, 10, c.n);
+        mbar_wait(&sh->s_full[g], (c.n >> 1) & 1);
+        tc_fence_after();
+        if (tracer) bw_trace(p, 1 + g, tr, 11, c.n);
+        const int c0 = c.chunk * BW_CW;
+        const int wc = min(BW_CW, p.sw - c0);
+        if (warp_has_rows) {
+          const uint32_t t_s = tmem + lane_addr + g * 192, t_dp = t_s + 96;
+          bwd_chunk<DKV>(t_s, t_dp, stat_saddr + c0 * 4, nl_row, de_row, c0, wc, p.N);
+          tmem_st_wait();
+        }
+        tc_fence_before();
+        mbar_arrive(&sh->p_full[g]);
+        if (tracer) bw_trace(p, 1 + g, tr, 12, c.n);
+
+        if (c.chunk == p.nc - 1) {
+          // ---- accumulators of this row tile -> HBM (this warpgroup handled the tile's last chunk)
+          const int acc = DKV ? 0 : (c.tcount & 1);
+          const uint32_t acc_use = DKV ? c.tcount : (c.tcount >> 1);
+          mbar_wait(&sh->acc_full[acc], acc_use & 1);
+          tc_fence_after();
+          if (tracer) bw_trace(p, 1 + g, tr, 13, c.n);
+          const int s = c.item / p.H, h = c.item % p.H;
+          __nv_bfloat16* grow = p.dqkv + (static_cast<long>(s) * p.N + row) * p.ld_qkv + h * 64;
+          if constexpr (DKV) {
+            uint32_t x0[32], x1[32];
+            if (warp_has_rows) {
+              tmem_ld_32x32b_x32(tmem + lane_addr + BW_ACC_COL, x0);
+              tmem_ld_32x32b_x32(tmem + lane_addr + BW_ACC_COL + 32, x1);
+              tmem_ld_wait();
+              if (row < p.N) store_row64_bf16(grow + 2 * p.D, x0, x1, 1.0f);     // dV
+              tmem_ld_32x32b_x32(tmem + lane_addr + BW_ACC_COL + 64, x0);
+              tmem_ld_32x32b_x32(tmem + lane_addr + BW_ACC_COL + 96, x1);
+              tmem_ld_wait();
+            }
+            tc_fence_before();
+            mbar_arrive(&sh->acc_empty[acc]);
+            if (warp_has_rows && row < p.N) store_row64_bf16(grow + p.D, x0, x1, 1.0f);   // dK
+          } else {
+            uint32_t x0[32], x1[32];
+            if (warp_has_rows) {
+              tmem_ld_32x32b_x32(tmem + lane_addr + BW_ACC_COL + acc * 64, x0);
+              tmem_ld_32x32b_x32(tmem + lane_addr + BW_ACC_COL + acc * 64 + 32, x1);
+              tmem_ld_wait();
+            }
+            tc_fence_before();
+            mbar_arrive(&sh->acc_empty[acc]);
+            if (warp_has_rows && row < p.N) store_row64_bf16(grow, x0, x1, p.q_scale);    // dQ
+          }
+          if (tracer) bw_trace(p, 1 + g, tr, 14, c.n);
+        }
+      }
+      c.advance(p);
+      if constexpr (DKV) {
+        if (c.it != it_now) mbar_arrive(&sh->stat_empty[it_now & 1]);   // done with that item's statistics
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc(tmem, 512);
+  }
+}
+
+// returns 0 if launched, -1 if the shape is not handled here (caller uses the general mma.sync
+// path), > 0 on error.  Expects delta to be filled already.
+int attention_bwd_tc(const missm_attn_args* a, cudaStream_t stream) {
+  const bool ok = !a->causal && a->key_mask == nullptr && a->s_in == 1 && a->tok_stride == 1 &&
+                  a->seq_outer == a->N && a->N <= BW_MAXN && a->N >= 16 && a->head_dim == 64;
+  if (!ok) return -1;
+  CUtensorMap tm128, tm16, td128, td16;
+  const uint64_t seq_q = static_cast<uint64_t>(a->N) * a->ld_qkv, seq_o = static_cast<uint64_t>(a->N) * a->ld_o;
+  if (int rc = make_tmap_3d_bf16(&tm128, a->qkv, 3 * static_cast<uint64_t>(a->D), a->N, a->n_seq, a->ld_qkv, seq_q, 64, 128)) return rc;
+  if (int rc = make_tmap_3d_bf16(&tm16, a->qkv, 3 * static_cast<uint64_t>(a->D), a->N, a->n_seq, a->ld_qkv, seq_q, 64, 16)) return rc;
+  if (int rc = make_tmap_3d_bf16(&td128, a->d_out, a->D, a->N, a->n_seq, a->ld_o, seq_o, 64, 128)) return rc;
+  if (int rc = make_tmap_3d_bf16(&td16, a->d_out, a->D, a->N, a->n_seq, a->ld_o, seq_o, 64, 16)) return rc;
+  AttnBwdTcParams p;
+  p.N = a->N, p.H = a->H, p.D = a->D, p.n_items = a->n_seq * a->H;
+  p.sw = (a->N + 15) / 16 * 16;
+  p.nt = (a->N + 127) / 128;
+  p.nc = (p.sw + BW_CW - 1) / BW_CW;
+  p.lse = a->lse, p.delta = a->delta;
+  p.dqkv = static_cast<__nv_bfloat16*>(a->dqkv), p.ld_qkv = a->ld_qkv, p.q_scale = a->q_scale;
+  const int smem = 4 * BW_RES_BYTES + 4 * BW_TILE_BYTES + 4 * BW_STAT * 4 + static_cast<int>(sizeof(AttnBwdSmem)) + 1024;
+  static bool configured = false;
+  if (!configured) {
+    MISSM_CHECK_CUDA(cudaFuncSetAttribute(attn_bwd_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    MISSM_CHECK_CUDA(cudaFuncSetAttribute(attn_bwd_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    configured = true;
+  }
+  const int grid = p.n_items < kNumSMs ? p.n_items : kNumSMs;
+  p.trace = nullptr;
+  const char* trace_path = getenv("MISSM_ATTN_TRACE");   // debugging aid: dumps CTA 0's event clocks (synchronises!)
+  if (trace_path != nullptr) {
+    const size_t nb = 2 * 3 * 330 * 3 * sizeof(long long);
+    long long* d = nullptr;
+    MISSM_CHECK_CUDA(cudaMalloc(&d, nb));
+    MISSM_CHECK_CUDA(cudaMemsetAsync(d, 0, nb, stream));
+    p.trace = d;
+    attn_bwd_tc_kernel<true><<<grid, BW_THREADS, smem, stream>>>(tm128, tm16, td128, td16, p);
+    p.trace = d + 3 * 330 * 3;
+    attn_bwd_tc_kernel<false><<<grid, BW_THREADS, smem, stream>>>(tm128, tm16, td128, td16, p);
+    MISSM_CHECK_CUDA(cudaStreamSynchronize(stream));
+    long long* h = static_cast<long long*>(malloc(nb));
+    MISSM_CHECK_CUDA(cudaMemcpy(h, d, nb, cudaMemcpyDeviceToHost));
+    if (FILE* f = fopen(trace_path, "w")) {
+      for (size_t i = 0; i < nb / 24; ++i)
+        if (h[3 * i] != 0) fprintf(f, "%zu %lld %lld %lld\n", i / 330, h[3 * i], h[3 * i + 1], h[3 * i + 2]);
+      fclose(f);
+    }
+    free(h);
+    cudaFree(d);
+    return 0;
+  }
+  attn_bwd_tc_kernel<true><<<grid, BW_THREADS, smem, stream>>>(tm128, tm16, td128, td16, p);
+  attn_bwd_tc_kernel<false><<<grid, BW_THREADS, smem, stream>>>(tm128, tm16, td128, td16, p);
+  MISSM_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+}  // namespace missm

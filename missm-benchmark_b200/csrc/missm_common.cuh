@@ -39,6 +39,21 @@ __device__ __forceinline__ uint32_t smem_u32(const void* p) {
   return static_cast<uint32_t>(__cvta_generic_to_shared(p));
 }
 __device__ __forceinline__ int lane_id() { return threadIdx.x & 31; }
+// One lane of a CONVERGED warp.  Single-thread work (tcgen05.mma / TMA issue) is written as
+// `if (elect_one_sync()) {...}` inside warp-uniform code rather than under `if (lane == 0)`: only
+// then does ptxas keep descriptors and TMEM addresses in uniform registers instead of wrapping every
+// UTCHMMA / UTMALDG in an ELECT + R2UR.BROADCAST + branch "waterfall" (~100 issue cycles each).
+__device__ __forceinline__ bool elect_one_sync() {
+  uint32_t pred = 0;
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "elect.sync _|p, 0xffffffff;\n"
+      "selp.u32 %0, 1, 0, p;\n"
+      "}\n"
+      : "=r"(pred));
+  return pred != 0;
+}
 
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
@@ -243,6 +258,18 @@ __device__ __forceinline__ void tmem_st_32x32b_x16(uint32_t taddr, const uint32_
       : "memory");
 }
 
+__device__ __forceinline__ void tmem_st_32x32b_x8(uint32_t taddr, const uint32_t (&r)[8]) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"r"(taddr),
+               "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7])
+               : "memory");
+}
+// 2^x on the MUFU pipe (ex2.approx.ftz: -inf -> +0, no denormal fix-up code around it)
+__device__ __forceinline__ float fast_ex2(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
 // ----------------------------------------------------------------------------------------
 // UMMA descriptors (PTX ISA "tcgen05 matrix descriptor" / "instruction descriptor")
 // ----------------------------------------------------------------------------------------
@@ -277,5 +304,8 @@ __host__ __device__ constexpr uint32_t umma_idesc_bf16_f32(int M, int N, int a_m
 // box = box_inner x box_outer, 128B swizzle (box_inner * 2 bytes must be <= 128).
 int make_tmap_2d_bf16(CUtensorMap* out, const void* base, uint64_t inner, uint64_t outer,
                       uint64_t ld_elems, uint32_t box_inner, uint32_t box_outer);
+// 3-D bf16 tensor (d0 contiguous; d1, d2 with element strides), box = b0 x b1 x 1, 128B swizzle
+int make_tmap_3d_bf16(CUtensorMap* out, const void* base, uint64_t d0, uint64_t d1, uint64_t d2,
+                      uint64_t stride1_elems, uint64_t stride2_elems, uint32_t b0, uint32_t b1);
 
 }  // namespace missm

@@ -1,0 +1,14 @@
+import sys, os
+sys.path.insert(0, os.path.join(os.path.dirname(__file__), "..", "missm-benchmark_b200"))
+import torch
+from missm_b200 import ops
+S,H,N=58,16,257; D=H*64
+torch.manual_seed(0)
+qkv=(torch.randn(S*N,3*D,device="cuda")*0.7).bfloat16()
+lay=ops.SeqLayout.spatial(S,N)
+d_out=torch.randn(S*N,D,device="cuda").bfloat16()
+for _ in range(2):
+    out,lse=ops.attention_fwd(qkv,lay,H)
+    dqkv=ops.attention_bwd(qkv,out,lse,d_out,lay,H,0.125)
+torch.cuda.synchronize()
+print("ok")
