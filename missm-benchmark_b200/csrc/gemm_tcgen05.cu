@@ -14,162 +14,15 @@
 //
 // Bound: tensor pipe.  Algorithmic work per launch = 2*M*N*K flop.
 #include <cstdarg>
+#include <cstdlib>
 #include <cstdio>
 #include <cstring>
 
 #include "../../include/missm_b200.h"
+#include "gemm_common.cuh"
 #include "missm_common.cuh"
 
 namespace missm {
-
-constexpr int BM = 128;
-constexpr int BK = 64;  // 64 bf16 = one 128-byte swizzle row
-constexpr int kEpiWarps = 8;                         // two per TMEM lane quarter
-constexpr int kGemmThreads = 128 + 32 * kEpiWarps;  // 4 control warps + epilogue warps
-constexpr int A_STAGE_BYTES = BM * BK * 2;
-
-struct GemmParams {
-  int M, N, K;
-  int num_m_blk, num_n_blk, num_splits, kblk_per_split, num_kblk;
-  int a_mn, b_mn;
-  void* C;
-  int ldc;
-  const float* bias;
-  float col_scale;
-  int scale_cols;
-  const void* aux_in;
-  int ld_aux_in;
-  void* aux_out;
-  int ld_aux_out;
-  int patch_P;
-  int atomic_out;
-};
-
-template <int BN>
-struct GemmCfg {
-  static constexpr int STAGES = (BN == 256) ? 4 : 6;
-  static constexpr int B_STAGE_BYTES = BN * BK * 2;
-  static constexpr int TMEM_COLS = 2 * BN;
-  static constexpr int SMEM_BYTES = STAGES * (A_STAGE_BYTES + B_STAGE_BYTES) + 1024 /*align*/ +
-                                    256 /*barriers + tmem slot*/;
-};
-
-// ---------------------------------------------------------------------------------------
-// epilogue for one row x 32 consecutive columns held in registers
-// ---------------------------------------------------------------------------------------
-template <int EPI, bool OUT_F32>
-__device__ __forceinline__ void epilogue_row32(const GemmParams& p, int row, int col0,
-                                               const uint32_t (&acc)[32]) {
-  const int ncols = min(32, p.N - col0);  // N % 8 == 0 is enforced by the host
-  float v[32];
-#pragma unroll
-  for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(acc[j]);
-
-  if (p.bias != nullptr) {
-#pragma unroll
-    for (int j = 0; j < 32; j += 4) {
-      if (j < ncols) {
-        float4 b = __ldg(reinterpret_cast<const float4*>(p.bias + col0 + j));
-        v[j] += b.x, v[j + 1] += b.y, v[j + 2] += b.z, v[j + 3] += b.w;
-      }
-    }
-  }
-
-  size_t out_row = static_cast<size_t>(row);
-  if constexpr (EPI == MISSM_EPI_LINEAR) {
-    if (p.scale_cols > 0) {
-#pragma unroll
-      for (int j = 0; j < 32; ++j)
-        if (col0 + j < p.scale_cols) v[j] *= p.col_scale;
-    }
-  } else if constexpr (EPI == MISSM_EPI_GELU) {
-    __nv_bfloat16* u = reinterpret_cast<__nv_bfloat16*>(p.aux_out) +
-                       static_cast<size_t>(row) * p.ld_aux_out + col0;
-#pragma unroll
-    for (int j = 0; j < 32; j += 8) {
-      if (j < ncols) {
-        uint4 q;
-        q.x = pack_bf16x2(v[j], v[j + 1]);
-        q.y = pack_bf16x2(v[j + 2], v[j + 3]);
-        q.z = pack_bf16x2(v[j + 4], v[j + 5]);
-        q.w = pack_bf16x2(v[j + 6], v[j + 7]);
-        *reinterpret_cast<uint4*>(u + j) = q;
-      }
-    }
-#pragma unroll
-    for (int j = 0; j < 32; ++j) v[j] = quick_gelu(v[j]);
-  } else if constexpr (EPI == MISSM_EPI_RESID) {
-    const float* r = reinterpret_cast<const float*>(p.aux_in) +
-                     static_cast<size_t>(row) * p.ld_aux_in + col0;
-#pragma unroll
-    for (int j = 0; j < 32; j += 4) {
-      if (j < ncols) {
-        float4 x = *reinterpret_cast<const float4*>(r + j);
-        v[j] += x.x, v[j + 1] += x.y, v[j + 2] += x.z, v[j + 3] += x.w;
-      }
-    }
-  } else if constexpr (EPI == MISSM_EPI_DGELU) {
-    const __nv_bfloat16* u = reinterpret_cast<const __nv_bfloat16*>(p.aux_in) +
-                             static_cast<size_t>(row) * p.ld_aux_in + col0;
-#pragma unroll
-    for (int j = 0; j < 32; j += 8) {
-      if (j < ncols) {
-        uint4 q = *reinterpret_cast<const uint4*>(u + j);
-        float2 a = unpack_bf16x2(q.x), b = unpack_bf16x2(q.y), c = unpack_bf16x2(q.z),
-               d = unpack_bf16x2(q.w);
-        v[j] *= quick_gelu_grad(a.x), v[j + 1] *= quick_gelu_grad(a.y);
-        v[j + 2] *= quick_gelu_grad(b.x), v[j + 3] *= quick_gelu_grad(b.y);
-        v[j + 4] *= quick_gelu_grad(c.x), v[j + 5] *= quick_gelu_grad(c.y);
-        v[j + 6] *= quick_gelu_grad(d.x), v[j + 7] *= quick_gelu_grad(d.y);
-      }
-    }
-  } else if constexpr (EPI == MISSM_EPI_PATCH) {
-    const int sample = row / p.patch_P, patch = row % p.patch_P;
-    out_row = static_cast<size_t>(sample) * (p.patch_P + 1) + 1 + patch;
-    const float* pos = reinterpret_cast<const float*>(p.aux_in) +
-                       static_cast<size_t>(1 + patch) * p.ld_aux_in + col0;
-#pragma unroll
-    for (int j = 0; j < 32; j += 4) {
-      if (j < ncols) {
-        float4 x = __ldg(reinterpret_cast<const float4*>(pos + j));
-        v[j] += x.x, v[j + 1] += x.y, v[j + 2] += x.z, v[j + 3] += x.w;
-      }
-    }
-  }
-
-  if constexpr (OUT_F32) {
-    float* c = reinterpret_cast<float*>(p.C) + out_row * p.ldc + col0;
-    if (p.atomic_out) {
-#pragma unroll
-      for (int j = 0; j < 32; j += 4) {
-        if (j < ncols) {
-          asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(c + j), "f"(v[j]),
-                       "f"(v[j + 1]), "f"(v[j + 2]), "f"(v[j + 3])
-                       : "memory");
-        }
-      }
-    } else {
-#pragma unroll
-      for (int j = 0; j < 32; j += 4) {
-        if (j < ncols)
-          *reinterpret_cast<float4*>(c + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
-      }
-    }
-  } else {
-    __nv_bfloat16* c = reinterpret_cast<__nv_bfloat16*>(p.C) + out_row * p.ldc + col0;
-#pragma unroll
-    for (int j = 0; j < 32; j += 8) {
-      if (j < ncols) {
-        uint4 q;
-        q.x = pack_bf16x2(v[j], v[j + 1]);
-        q.y = pack_bf16x2(v[j + 2], v[j + 3]);
-        q.z = pack_bf16x2(v[j + 4], v[j + 5]);
-        q.w = pack_bf16x2(v[j + 6], v[j + 7]);
-        *reinterpret_cast<uint4*>(c + j) = q;
-      }
-    }
-  }
-}
 
 // ---------------------------------------------------------------------------------------
 // kernel
@@ -192,6 +45,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA,
   uint64_t* tfull_bar = empty_bar + STAGES;
   uint64_t* tempty_bar = tfull_bar + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+  uint8_t* sStage = reinterpret_cast<uint8_t*>(full_bar) + 256;   // kEpiWarps x 4 KB epilogue staging
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -225,7 +79,9 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA,
 
   if (warp == 0) {
     // ================================ TMA producer ====================================
-    if (lane == 0) {
+    // (the converged warp walks the schedule and waits; one elected lane arms + issues, see
+    //  elect_one_sync() in missm_common.cuh)
+    {
       int stage = 0;
       uint32_t phase = 0;
       for (int w = blockIdx.x; w < total_work; w += gridDim.x) {
@@ -235,38 +91,44 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA,
         const int kb1 = min(kb0 + p.kblk_per_split, p.num_kblk);
         for (int kb = kb0; kb < kb1; ++kb) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
-          mbar_arrive_expect_tx(&full_bar[stage], A_STAGE_BYTES + B_STAGE_BYTES);
-          uint8_t* a_dst = sA + stage * A_STAGE_BYTES;
-          uint8_t* b_dst = sB + stage * B_STAGE_BYTES;
-          if (!p.a_mn) {
-            tma_load_2d(a_dst, &tmA, &full_bar[stage], kb * BK, m_blk * BM);
-          } else {
+          if (elect_one_sync()) {
+            mbar_arrive_expect_tx(&full_bar[stage], A_STAGE_BYTES + B_STAGE_BYTES);
+            uint8_t* a_dst = sA + stage * A_STAGE_BYTES;
+            uint8_t* b_dst = sB + stage * B_STAGE_BYTES;
+            if (!p.a_mn) {
+              tma_load_2d(a_dst, &tmA, &full_bar[stage], kb * BK, m_blk * BM);
+            } else {
 #pragma unroll
-            for (int j = 0; j < BM / 64; ++j)
-              tma_load_2d(a_dst + j * (BK * 128), &tmA, &full_bar[stage], m_blk * BM + j * 64,
-                          kb * BK);
-          }
-          if (!p.b_mn) {
-            tma_load_2d(b_dst, &tmB, &full_bar[stage], kb * BK, n_blk * BN);
-          } else {
+              for (int j = 0; j < BM / 64; ++j)
+                tma_load_2d(a_dst + j * (BK * 128), &tmA, &full_bar[stage], m_blk * BM + j * 64,
+                            kb * BK);
+            }
+            if (!p.b_mn) {
+              tma_load_2d(b_dst, &tmB, &full_bar[stage], kb * BK, n_blk * BN);
+            } else {
 #pragma unroll
-            for (int j = 0; j < BN / 64; ++j)
-              tma_load_2d(b_dst + j * (BK * 128), &tmB, &full_bar[stage], n_blk * BN + j * 64,
-                          kb * BK);
+              for (int j = 0; j < BN / 64; ++j)
+                tma_load_2d(b_dst + j * (BK * 128), &tmB, &full_bar[stage], n_blk * BN + j * 64,
+                            kb * BK);
+            }
           }
+          __syncwarp();
           if (++stage == STAGES) stage = 0, phase ^= 1;
         }
       }
     }
   } else if (warp == 1) {
     // ================================ MMA issuer ======================================
-    if (lane == 0) {
+    {
       const uint32_t idesc = umma_idesc_bf16_f32(BM, BN, p.a_mn, p.b_mn);
       // K-major SW128: rows of 128 B, 8-row groups 1024 B apart (SBO); K step of 16 = +32 B.
       // MN-major SW128: 64-element MN chunks (BK rows x 128 B) LBO apart, 8-k-row groups 1024 B
       // apart (SBO); K step of 16 = +16 rows = +2048 B.
       const uint32_t a_lbo = p.a_mn ? BK * 128 : 16, b_lbo = p.b_mn ? BK * 128 : 16;
-      const uint32_t a_kstep = p.a_mn ? 2048 : 32, b_kstep = p.b_mn ? 2048 : 32;
+      const uint32_t a_kstep = (p.a_mn ? 2048 : 32) >> 4, b_kstep = (p.b_mn ? 2048 : 32) >> 4;
+      // descriptors of all stages differ only in the (16-byte granular) start address field
+      const uint64_t a_desc0 = umma_smem_desc_sw128(smem_u32(sA), a_lbo, 1024);
+      const uint64_t b_desc0 = umma_smem_desc_sw128(smem_u32(sB), b_lbo, 1024);
       int stage = 0;
       uint32_t phase = 0;
       int acc = 0;
@@ -281,18 +143,19 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA,
         for (int kb = kb0; kb < kb1; ++kb) {
           mbar_wait(&full_bar[stage], phase);
           tc_fence_after();
-          const uint32_t a_base = smem_u32(sA + stage * A_STAGE_BYTES);
-          const uint32_t b_base = smem_u32(sB + stage * B_STAGE_BYTES);
+          if (elect_one_sync()) {
+            const uint64_t a_desc = a_desc0 + stage * (A_STAGE_BYTES >> 4);
+            const uint64_t b_desc = b_desc0 + stage * (B_STAGE_BYTES >> 4);
 #pragma unroll
-          for (int k = 0; k < BK / 16; ++k) {
-            const uint64_t a_desc = umma_smem_desc_sw128(a_base + k * a_kstep, a_lbo, 1024);
-            const uint64_t b_desc = umma_smem_desc_sw128(b_base + k * b_kstep, b_lbo, 1024);
-            umma_f16_ss(d_tmem, a_desc, b_desc, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+            for (int k = 0; k < BK / 16; ++k)
+              umma_f16_ss(d_tmem, a_desc + k * a_kstep, b_desc + k * b_kstep, idesc,
+                          (kb > kb0 || k > 0) ? 1u : 0u);
+            umma_commit(&empty_bar[stage]);  // frees the smem slot once these MMAs retire
+            if (kb == kb1 - 1) umma_commit(&tfull_bar[acc]);  // accumulator complete -> epilogue
           }
-          umma_commit(&empty_bar[stage]);  // frees the smem slot once these MMAs retire
+          __syncwarp();
           if (++stage == STAGES) stage = 0, phase ^= 1;
         }
-        umma_commit(&tfull_bar[acc]);  // accumulator complete -> epilogue
         if (++acc == 2) acc = 0, acc_phase ^= 1;
       }
     }
@@ -300,6 +163,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA,
     // ================================ epilogue ========================================
     const int q = warp & 3;               // TMEM lane quarter this warp may access
     const int half = (warp - 4) >> 2;     // the two warps of a quarter split the column chunks
+    uint8_t* stage = sStage + (warp - 4) * kEpiStageBytes;
     int acc = 0;
     uint32_t acc_phase = 0;
     for (int w = blockIdx.x; w < total_work; w += gridDim.x) {
@@ -307,7 +171,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA,
       const int n_blk = rem / p.num_m_blk, m_blk = rem % p.num_m_blk;
       mbar_wait(&tfull_bar[acc], acc_phase);
       tc_fence_after();
-      const int row = m_blk * BM + q * 32 + lane;
+      const int row0 = m_blk * BM + q * 32;
       const uint32_t t_row = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * BN;
 #pragma unroll 1
       for (int c = half; c < BN / 32; c += kEpiWarps / 4) {
@@ -316,7 +180,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA,
         uint32_t r[32];
         tmem_ld_32x32b_x32(t_row + c * 32, r);
         tmem_ld_wait();
-        if (row < p.M) epilogue_row32<EPI, OUT_F32>(p, row, col0, r);
+        if (row0 < p.M) epilogue_chunk<EPI, OUT_F32>(p, row0, col0, r, stage, lane);   // warp-uniform
       }
       tc_fence_before();
       __syncwarp();
@@ -440,6 +304,9 @@ static int dispatch_epi(int epi, bool out_f32, const CUtensorMap& a, const CUten
 
 }  // namespace missm
 
+namespace missm {
+int gemm_launch_2cta(const missm_gemm_args* a, GemmParams p, cudaStream_t stream);  // gemm_tcgen05_2cta.cu
+}
 using namespace missm;
 
 extern "C" int missm_version(void) { return MISSM_ABI_VERSION; }
@@ -468,6 +335,10 @@ extern "C" int missm_gemm_bf16(const missm_gemm_args* a, void* stream_v) {
   p.aux_in = a->aux_in, p.ld_aux_in = a->ld_aux_in;
   p.aux_out = a->aux_out, p.ld_aux_out = a->ld_aux_out;
   p.patch_P = a->patch_P;
+  // large-M problems go to the CTA-pair kernel (gemm_tcgen05_2cta.cu); MISSM_GEMM_1CTA=1 keeps
+  // everything on the single-CTA kernel (A/B measurements)
+  static const bool only_1cta = getenv("MISSM_GEMM_1CTA") != nullptr;
+  if (!only_1cta && a->M >= 1024) return gemm_launch_2cta(a, p, stream);
   p.num_m_blk = (a->M + BM - 1) / BM;
   p.num_kblk = (a->K + BK - 1) / BK;
 

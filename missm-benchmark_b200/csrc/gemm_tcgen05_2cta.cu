@@ -1,0 +1,291 @@
+// CTA-pair tcgen05 GEMM for sm_100a (tcgen05.mma.cta_group::2): the large-M path of missm_gemm_bf16.
+//
+//   C[m,n] = epilogue( sum_k A[m,k] * B[n,k] ),  bf16 operands, fp32 accumulation in TMEM.
+//
+// Why a second kernel: with one CTA per tile (gemm_tcgen05.cu) every 128x256x16 MMA reads 12 KB of
+// shared memory per 128 tensor cycles while TMA writes the same amount -- 187 B/cycle against a
+// 128 B/cycle shared-memory port, which caps that kernel near 2/3 of the tensor peak (measured
+// 1.32 PFLOP/s at 8192^3, cuBLAS 1.66).  Here two CTAs on the two SMs of a TPC (cluster of 2) share
+// one 256 x BN tile: each loads its own 128 rows of A and only HALF of the B tile, and a single
+// MMA issued by the leader drives both tensor cores (M = 256), so shared-memory traffic per SM
+// drops by a third and the B operand is fetched from L2 once per pair.
+//
+// Roles per CTA (384 threads, persistent over pair tiles):
+//   warp 0 : TMA producer (both CTAs; transaction bytes complete on the LEADER's full barrier)
+//   warp 1 : MMA issuer (leader CTA only; commits multicast to both CTAs' barriers)
+//   warp 2 : TMEM allocator (cta_group::2, both CTAs)
+//   warps 4..11 : epilogue, each CTA drains its own 128 accumulator rows (same fused epilogues as the
+//                 1-CTA kernel); "accumulator free" arrives on the leader's barrier across the cluster
+// Bound: tensor pipe.  Algorithmic work per launch = 2*M*N*K flop.
+#include "../../include/missm_b200.h"
+#include "gemm_common.cuh"
+#include "missm_common.cuh"
+
+namespace missm {
+
+template <int BN>
+struct Gemm2Cfg {
+  static constexpr int B_HALF_BYTES = (BN / 2) * BK * 2;
+  static constexpr int STAGE_BYTES = A_STAGE_BYTES + B_HALF_BYTES;
+  static constexpr int STAGES = (BN == 256) ? 6 : 8;
+  static constexpr int TMEM_COLS = 2 * BN;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers + tmem slot*/ +
+                                    kEpiWarps * kEpiStageBytes /*epilogue staging*/;
+};
+
+template <int BN, int EPI, bool OUT_F32>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kGemmThreads, 1)
+gemm_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                         const GemmParams p) {
+  using Cfg = Gemm2Cfg<BN>;
+  constexpr int STAGES = Cfg::STAGES;
+  constexpr int B_HALF_BYTES = Cfg::B_HALF_BYTES;
+
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
+  uint8_t* sA = smem;
+  uint8_t* sB = smem + STAGES * A_STAGE_BYTES;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(sB + STAGES * B_HALF_BYTES);
+  uint64_t* empty_bar = full_bar + STAGES;
+  uint64_t* tfull_bar = empty_bar + STAGES;
+  uint64_t* tempty_bar = tfull_bar + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+  uint8_t* sStage = reinterpret_cast<uint8_t*>(full_bar) + 256;   // kEpiWarps x 4 KB epilogue staging
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();          // 0 = leader
+  const int pair = blockIdx.x >> 1, num_pairs = gridDim.x >> 1;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int i = 0; i < STAGES; ++i) {
+      mbar_init(&full_bar[i], 1);      // leader's copy is the live one: its producer arms it
+      mbar_init(&empty_bar[i], 1);     // one multicast commit per use
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&tfull_bar[i], 1);
+      mbar_init(&tempty_bar[i], 2 * kEpiWarps);   // leader's copy: epilogue warps of BOTH CTAs
+    }
+    fence_mbar_init();
+  }
+  if (warp == 2) {
+    tmem_alloc_2cta(tmem_slot, Cfg::TMEM_COLS);
+    tmem_relinquish_2cta();
+  }
+  tc_fence_before();
+  cluster_sync_all();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  const int tiles_mn = p.num_m_blk * p.num_n_blk;   // num_m_blk counts 256-row pair tiles here
+  const int total_work = tiles_mn * p.num_splits;
+
+  if (warp == 0) {
+    // ================================ TMA producer (both CTAs) ========================
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int w = pair; w < total_work; w += num_pairs) {
+      const int split = w / tiles_mn, rem = w % tiles_mn;
+      const int n_blk = rem / p.num_m_blk, m_blk = rem % p.num_m_blk;
+      const int m0 = m_blk * 256 + static_cast<int>(rank) * 128;
+      const int n0 = n_blk * BN + static_cast<int>(rank) * (BN / 2);
+      const int kb0 = split * p.kblk_per_split;
+      const int kb1 = min(kb0 + p.kblk_per_split, p.num_kblk);
+      for (int kb = kb0; kb < kb1; ++kb) {
+        mbar_wait(&empty_bar[stage], phase ^ 1);
+        if (elect_one_sync()) {
+          if (rank == 0) mbar_arrive_expect_tx(&full_bar[stage], 2 * Cfg::STAGE_BYTES);
+          const uint32_t bar = mapa_shared(smem_u32(&full_bar[stage]), 0);
+          uint8_t* a_dst = sA + stage * A_STAGE_BYTES;
+          uint8_t* b_dst = sB + stage * B_HALF_BYTES;
+          if (!p.a_mn) {
+            tma_load_2d_2cta(a_dst, &tmA, bar, kb * BK, m0);
+          } else {
+#pragma unroll
+            for (int j = 0; j < BM / 64; ++j) tma_load_2d_2cta(a_dst + j * (BK * 128), &tmA, bar, m0 + j * 64, kb * BK);
+          }
+          if (!p.b_mn) {
+            tma_load_2d_2cta(b_dst, &tmB, bar, kb * BK, n0);
+          } else {
+#pragma unroll
+            for (int j = 0; j < BN / 128; ++j) tma_load_2d_2cta(b_dst + j * (BK * 128), &tmB, bar, n0 + j * 64, kb * BK);
+          }
+        }
+        __syncwarp();
+        if (++stage == STAGES) stage = 0, phase ^= 1;
+      }
+    }
+  } else if (warp == 1) {
+    // ================================ MMA issuer (leader only) ========================
+    if (rank == 0) {
+      const uint32_t idesc = umma_idesc_bf16_f32(256, BN, p.a_mn, p.b_mn);
+      const uint32_t a_lbo = p.a_mn ? BK * 128 : 16, b_lbo = p.b_mn ? BK * 128 : 16;
+      const uint32_t a_kstep = (p.a_mn ? 2048 : 32) >> 4, b_kstep = (p.b_mn ? 2048 : 32) >> 4;
+      const uint64_t a_desc0 = umma_smem_desc_sw128(smem_u32(sA), a_lbo, 1024);
+      const uint64_t b_desc0 = umma_smem_desc_sw128(smem_u32(sB), b_lbo, 1024);
+      int stage = 0;
+      uint32_t phase = 0;
+      int acc = 0;
+      uint32_t acc_phase = 0;
+      for (int w = pair; w < total_work; w += num_pairs) {
+        const int split = w / tiles_mn;
+        const int kb0 = split * p.kblk_per_split;
+        const int kb1 = min(kb0 + p.kblk_per_split, p.num_kblk);
+        mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * BN;
+        for (int kb = kb0; kb < kb1; ++kb) {
+          mbar_wait(&full_bar[stage], phase);
+          tc_fence_after();
+          if (elect_one_sync()) {
+            const uint64_t a_desc = a_desc0 + stage * (A_STAGE_BYTES >> 4);
+            const uint64_t b_desc = b_desc0 + stage * (B_HALF_BYTES >> 4);
+#pragma unroll
+            for (int k = 0; k < BK / 16; ++k)
+              umma_f16_ss_2cta(d_tmem, a_desc + k * a_kstep, b_desc + k * b_kstep, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+            umma_commit_2cta(&empty_bar[stage]);                      // frees the slot in both CTAs
+            if (kb == kb1 - 1) umma_commit_2cta(&tfull_bar[acc]);     // accumulator complete -> both epilogues
+          }
+          __syncwarp();
+          if (++stage == STAGES) stage = 0, phase ^= 1;
+        }
+        if (++acc == 2) acc = 0, acc_phase ^= 1;
+      }
+    }
+  } else if (warp >= 4) {
+    // ================================ epilogue (both CTAs, own 128 rows) ==============
+    const int q = warp & 3;
+    const int half = (warp - 4) >> 2;
+    uint8_t* stage = sStage + (warp - 4) * kEpiStageBytes;
+    const uint32_t tempty_leader0 = mapa_shared(smem_u32(&tempty_bar[0]), 0);
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int w = pair; w < total_work; w += num_pairs) {
+      const int rem = w % tiles_mn;
+      const int n_blk = rem / p.num_m_blk, m_blk = rem % p.num_m_blk;
+      mbar_wait(&tfull_bar[acc], acc_phase);
+      tc_fence_after();
+      const int row0 = m_blk * 256 + static_cast<int>(rank) * 128 + q * 32;
+      const uint32_t t_row = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * BN;
+#pragma unroll 1
+      for (int c = half; c < BN / 32; c += kEpiWarps / 4) {
+        const int col0 = n_blk * BN + c * 32;
+        if (col0 >= p.N) break;  // warp-uniform
+        uint32_t r[32];
+        tmem_ld_32x32b_x32(t_row + c * 32, r);
+        tmem_ld_wait();
+        if (row0 < p.M) epilogue_chunk<EPI, OUT_F32>(p, row0, col0, r, stage, lane);   // warp-uniform
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_cluster(tempty_leader0 + acc * 8);
+      if (++acc == 2) acc = 0, acc_phase ^= 1;
+    }
+  }
+
+  // neither CTA may leave (or free TMEM) while its partner can still touch its barriers / memory
+  tc_fence_before();
+  cluster_sync_all();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc_2cta(tmem_base, Cfg::TMEM_COLS);
+  }
+}
+
+template <int BN, int EPI, bool OUT_F32>
+static int launch_gemm2(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmParams& p, int grid,
+                        cudaStream_t stream) {
+  using Cfg = Gemm2Cfg<BN>;
+  auto kern = gemm_tcgen05_2cta_kernel<BN, EPI, OUT_F32>;
+  static bool configured = false;  // benign race: the attribute call is idempotent
+  if (!configured) {
+    MISSM_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
+    configured = true;
+  }
+  kern<<<grid, kGemmThreads, Cfg::SMEM_BYTES, stream>>>(tmA, tmB, p);
+  MISSM_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+template <int BN>
+static int dispatch_epi2(int epi, bool out_f32, const CUtensorMap& a, const CUtensorMap& b, const GemmParams& p,
+                         int grid, cudaStream_t s) {
+  switch (epi) {
+    case MISSM_EPI_LINEAR:
+      return out_f32 ? launch_gemm2<BN, MISSM_EPI_LINEAR, true>(a, b, p, grid, s)
+                     : launch_gemm2<BN, MISSM_EPI_LINEAR, false>(a, b, p, grid, s);
+    case MISSM_EPI_GELU:
+      return launch_gemm2<BN, MISSM_EPI_GELU, false>(a, b, p, grid, s);
+    case MISSM_EPI_RESID:
+      return launch_gemm2<BN, MISSM_EPI_RESID, true>(a, b, p, grid, s);
+    case MISSM_EPI_DGELU:
+      return launch_gemm2<BN, MISSM_EPI_DGELU, false>(a, b, p, grid, s);
+    case MISSM_EPI_PATCH:
+      return launch_gemm2<BN, MISSM_EPI_PATCH, true>(a, b, p, grid, s);
+  }
+  MISSM_REQUIRE(false, "unknown epilogue %d", epi);
+}
+
+// Called by missm_gemm_bf16 (gemm_tcgen05.cu) after argument validation; `p` carries everything but
+// the tiling.  Returns -1 if this path declines the shape.
+int gemm_launch_2cta(const missm_gemm_args* a, GemmParams p, cudaStream_t stream) {
+  constexpr int kPairs = kNumSMs / 2;
+  p.num_m_blk = (a->M + 255) / 256;
+  p.num_kblk = (a->K + BK - 1) / BK;
+  auto waves_eff = [&](int bn) {
+    long tiles = static_cast<long>(p.num_m_blk) * ((a->N + bn - 1) / bn);
+    long waves = (tiles + kPairs - 1) / kPairs;
+    return static_cast<double>(tiles) * bn / (static_cast<double>(waves) * kPairs * 256.0);
+  };
+  int bn = 256;
+  if (a->force_bn == 128 || a->force_bn == 256)
+    bn = a->force_bn;
+  else if (a->N <= 128 || waves_eff(128) > 1.15 * waves_eff(256))
+    bn = 128;
+  p.num_n_blk = (a->N + bn - 1) / bn;
+
+  const long tiles = static_cast<long>(p.num_m_blk) * p.num_n_blk;
+  int splits = 1;
+  const bool may_split = (a->epilogue == MISSM_EPI_LINEAR && a->out_f32 && a->bias == nullptr &&
+                          a->scale_cols == 0 && a->split_k != 1);
+  if (may_split) {
+    if (a->split_k > 1) {
+      splits = a->split_k;
+    } else if (tiles * 2 <= kPairs && p.num_kblk >= 16) {
+      splits = static_cast<int>((2L * kPairs + tiles - 1) / tiles);
+      if (splits > p.num_kblk / 8) splits = p.num_kblk / 8;
+    }
+    if (splits > p.num_kblk) splits = p.num_kblk;
+    if (splits < 1) splits = 1;
+  }
+  p.kblk_per_split = (p.num_kblk + splits - 1) / splits;
+  p.num_splits = (p.num_kblk + p.kblk_per_split - 1) / p.kblk_per_split;
+  p.atomic_out = p.num_splits > 1 ? 1 : 0;
+  if (p.atomic_out) {
+    MISSM_CHECK_CUDA(cudaMemset2DAsync(a->C, static_cast<size_t>(a->ldc) * 4, 0, static_cast<size_t>(a->N) * 4, a->M,
+                                       stream));
+  }
+
+  CUtensorMap tmA, tmB;
+  int rc;
+  if (!p.a_mn)
+    rc = make_tmap_2d_bf16(&tmA, a->A, a->K, a->M, a->lda, BK, BM);
+  else
+    rc = make_tmap_2d_bf16(&tmA, a->A, a->M, a->K, a->lda, 64, BK);
+  if (rc) return rc;
+  if (!p.b_mn)
+    rc = make_tmap_2d_bf16(&tmB, a->B, a->K, a->N, a->ldb, BK, bn / 2);
+  else
+    rc = make_tmap_2d_bf16(&tmB, a->B, a->N, a->K, a->ldb, 64, BK);
+  if (rc) return rc;
+
+  const long work = tiles * p.num_splits;
+  const int grid = 2 * static_cast<int>(work < kPairs ? work : kPairs);
+  if (bn == 256) return dispatch_epi2<256>(a->epilogue, a->out_f32 != 0, tmA, tmB, p, grid, stream);
+  return dispatch_epi2<128>(a->epilogue, a->out_f32 != 0, tmA, tmB, p, grid, stream);
+}
+
+}  // namespace missm
