@@ -258,8 +258,11 @@ def run_gpu_arm(a):
     # roofline of the dominant kernel (tcgen05 GEMM): CUDA events around every GEMM launch of one
     # more step on the launching stream (kept out of the headline so the events cost nothing there)
     ops.GEMM_TIMING = []
+    streams_on = model.encoder.tower_streams
+    model.encoder.tower_streams = False       # one stream: every GEMM is timed alone, not overlapped with another tower's
     step_resident()
     torch.cuda.synchronize()
+    model.encoder.tower_streams = streams_on
     g_ms = sum(e0.elapsed_time(e1) for e0, e1, _ in ops.GEMM_TIMING)
     g_flop = sum(f for _, _, f in ops.GEMM_TIMING)
     n_gemm = len(ops.GEMM_TIMING)
@@ -304,7 +307,7 @@ def run_gpu_arm(a):
             "warmup": max(a.warmup, 3), "ms_per_step": ms / a.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
             "config": {"workload": WORKLOAD, "batch_per_gpu": B, "missing_ratio": a.missing,
-                       "missing_samples": n_missing, "fusion": "sum", "layers": a.layers,
+                       "missing_samples": n_missing, "fusion": "sum", "layers": a.layers, "tower_streams": bool(model.encoder.tower_streams),
                        "step": "zero_grad + forward + CrossEntropy + backward (DDP allreduce at N>1); optimizer excluded (metric is fwd+bwd)",
                        "l2": "working set >> 126 MB L2 every step (1.8 GB bf16 weights + >30 GB activations)",
                        "encoder_tflops_algorithmic": algo_tf,

@@ -1,5 +1,6 @@
 """The encoder bank: drop-in for `languagebind.LanguageBind` (languagebind/__init__.py:54-85)
 with missing-modality mask compaction in front of every tower."""
+import contextlib
 import os
 
 import torch
@@ -65,6 +66,7 @@ class LanguageBind(nn.Module):
         self.modality_encoder = nn.ModuleDict(self.modality_encoder)
         self.modality_proj = nn.ModuleDict(self.modality_proj)
         self.compaction = os.environ.get("MISSM_COMPACTION", "1") != "0"
+        self.tower_streams = os.environ.get("MISSM_TOWER_STREAMS", "1") != "0"
 
     @classmethod
     def from_models(cls, models, use_temp=True):
@@ -80,7 +82,19 @@ class LanguageBind(nn.Module):
         enc['language'], proj['language'] = model.text_model, model.text_projection
         self.modality_encoder, self.modality_proj = nn.ModuleDict(enc), nn.ModuleDict(proj)
         self.compaction = os.environ.get("MISSM_COMPACTION", "1") != "0"
+        self.tower_streams = os.environ.get("MISSM_TOWER_STREAMS", "1") != "0"
         return self
+
+    def _side_streams(self, n, device):
+        """One CUDA stream per tower.  The towers are independent until the fusion head, and every hot
+        kernel is a persistent one-CTA-per-SM grid whose last wave leaves SMs idle (e.g. 236 pair tiles on
+        74 CTA pairs = 3.2 waves); with the towers on separate streams the next tower's CTAs fill those
+        SMs.  autograd replays each tower's backward on the stream its forward ran on."""
+        pool = self.__dict__.setdefault('_stream_pool', {})
+        key = (device.index, n)
+        if key not in pool:
+            pool[key] = [torch.cuda.Stream(device=device) for _ in range(n)]
+        return pool[key]
 
     def _scale(self, key):
         if self.use_temp and key != 'language':
@@ -107,20 +121,39 @@ class LanguageBind(nn.Module):
                 if counts[i] < B:
                     plan[k] = (idx[i], slot[i], counts[i], B)
         outputs = {}
-        for key in keys:
+        dev = None
+        for v in inputs.values():
+            for t in v.values():
+                if torch.is_tensor(t) and t.is_cuda:
+                    dev = t.device
+        use_streams = self.tower_streams and len(keys) > 1 and dev is not None
+        main = torch.cuda.current_stream(dev) if use_streams else None
+        streams = self._side_streams(len(keys), dev) if use_streams else None
+        for i, key in enumerate(keys):
             value = inputs[key]
             enc, proj = self.modality_encoder[key], self.modality_proj[key]
             scale = self._scale(key)
-            if key in plan:
-                pidx, slot, n, B = plan[key]
-                if n == 0:
-                    params = [p for p in list(enc.parameters()) + list(proj.parameters())]
-                    outputs[key] = _ZeroTower.apply(B, proj.weight.shape[0], proj.weight.device, *params)
-                    continue
-                y = enc(**value, present_idx=pidx, n_present=n, proj=proj, scale=scale)[1]
-                outputs[key] = ag.ScatterZeroFn.apply(y, slot, pidx, n, B)
+            if use_streams:
+                streams[i].wait_stream(main)
+                ctx = torch.cuda.stream(streams[i])
             else:
-                outputs[key] = enc(**value, proj=proj, scale=scale)[1]
+                ctx = contextlib.nullcontext()
+            with ctx:
+                if key in plan:
+                    pidx, slot, n, B = plan[key]
+                    if n == 0:
+                        params = [p for p in list(enc.parameters()) + list(proj.parameters())]
+                        outputs[key] = _ZeroTower.apply(B, proj.weight.shape[0], proj.weight.device, *params)
+                    else:
+                        y = enc(**value, present_idx=pidx, n_present=n, proj=proj, scale=scale)[1]
+                        outputs[key] = ag.ScatterZeroFn.apply(y, slot, pidx, n, B)
+                else:
+                    outputs[key] = enc(**value, proj=proj, scale=scale)[1]
+            if use_streams:
+                outputs[key].record_stream(main)
+        if use_streams:
+            for st in streams:
+                main.wait_stream(st)
         return outputs
 
 
