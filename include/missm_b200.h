@@ -23,7 +23,7 @@
 extern "C" {
 #endif
 
-#define MISSM_ABI_VERSION 1
+#define MISSM_ABI_VERSION 2
 
 int missm_version(void);
 const char* missm_last_error(void);
@@ -67,6 +67,8 @@ typedef struct missm_gemm_args {
   int32_t patch_P;    /* PATCH: patches per sample */
   int32_t split_k;    /* 0 = auto (only LINEAR + out_f32 + no bias may split), 1 = never */
   int32_t force_bn;   /* 0 = auto, 128 or 256 = force tile N */
+  float* colsum_out;  /* optional [N], PRE-ZEROED: += column sums over m of the fp32 value that is written
+                         to C (bias gradient of the consumer layer, fused into the producing GEMM) */
 } missm_gemm_args;
 
 int missm_gemm_bf16(const missm_gemm_args* args, void* stream);
@@ -113,12 +115,13 @@ int missm_layernorm_fwd(const float* x, int64_t ldx, const int32_t* row_index,
                         float* mean, float* rstd, int32_t M, int32_t D, float eps, void* stream);
 int missm_ln_bwd_num_partials(int32_t M);
 /* dx[row_index? row_index[r] : r] = (dres ? dres : 0) + LN'(dy); partial = workspace of
- * missm_ln_bwd_num_partials(M) * 2 * D floats; dgamma, dbeta = [D]. */
+ * missm_ln_bwd_num_partials(M) * 3 * D floats; dgamma, dbeta = [D]; dx_colsum (optional, [D]) =
+ * sum over the written rows of dx (the bias gradient of the Linear that produced this stream). */
 int missm_layernorm_bwd(const void* dy, int64_t lddy, int32_t dy_bf16, const float* x, int64_t ldx,
                         const int32_t* row_index, const float* mean, const float* rstd,
                         const float* gamma, const float* dres, float* dx, void* dx_bf16,
-                        float* partial, float* dgamma, float* dbeta, int32_t M, int32_t D,
-                        void* stream);
+                        float* partial, float* dgamma, float* dbeta, float* dx_colsum, int32_t M,
+                        int32_t D, void* stream);
 int missm_reduce_partials(const float* partial, int32_t R, int64_t stride, float* out, int32_t n,
                           float scale, void* stream);
 

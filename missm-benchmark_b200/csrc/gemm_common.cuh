@@ -27,6 +27,7 @@ struct GemmParams {
   int ld_aux_out;
   int patch_P;
   int atomic_out;
+  float* colsum_out;
 };
 
 template <int BN>
@@ -154,6 +155,22 @@ __device__ __forceinline__ void tile_stg(void* base, long ld, int col0, int ncol
   }
 }
 
+// sum over the 32 lanes of v[c] for every column c: butterfly "transpose-reduce" (31 shuffles);
+// returns in lane l the total of column l.  Destroys v.
+__device__ __forceinline__ float warp_colsum32(float (&v)[32], int lane) {
+#pragma unroll
+  for (int s = 16; s >= 1; s >>= 1) {
+    const bool up = (lane & s) != 0;
+#pragma unroll
+    for (int i = 0; i < s; ++i) {
+      const float send = up ? v[i] : v[i + s];
+      const float keep = up ? v[i + s] : v[i];
+      v[i] = keep + __shfl_xor_sync(0xffffffffu, send, s);
+    }
+  }
+  return v[0];
+}
+
 // `row0`: global row of this warp's lane 0; `acc`: this thread's row (row0 + lane) of the fp32
 // accumulator, columns [col0, col0 + 32).  All 32 lanes must call (warp-collective).
 template <int EPI, bool OUT_F32>
@@ -215,6 +232,14 @@ __device__ __forceinline__ void epilogue_chunk(const GemmParams& p, int row0, in
   }
 
   tile_row_write<OUT_F32>(stage, lane, v);
+  if (p.colsum_out != nullptr) {   // warp-uniform
+    if (row0 + lane >= p.M) {
+#pragma unroll
+      for (int j = 0; j < 32; ++j) v[j] = 0.f;
+    }
+    const float cs = warp_colsum32(v, lane);
+    if (lane < ncols) atomicAdd(p.colsum_out + col0 + lane, cs);
+  }
   __syncwarp();
   if constexpr (EPI == MISSM_EPI_PATCH)
     tile_stg<OUT_F32>(p.C, p.ldc, col0, ncols, RowMapPatchOut{row0, p.M, p.patch_P}, stage, lane, false);

@@ -335,6 +335,7 @@ extern "C" int missm_gemm_bf16(const missm_gemm_args* a, void* stream_v) {
   p.aux_in = a->aux_in, p.ld_aux_in = a->ld_aux_in;
   p.aux_out = a->aux_out, p.ld_aux_out = a->ld_aux_out;
   p.patch_P = a->patch_P;
+  p.colsum_out = a->colsum_out;
   // large-M problems go to the CTA-pair kernel (gemm_tcgen05_2cta.cu); MISSM_GEMM_1CTA=1 keeps
   // everything on the single-CTA kernel (A/B measurements)
   static const bool only_1cta = getenv("MISSM_GEMM_1CTA") != nullptr;
@@ -359,7 +360,7 @@ extern "C" int missm_gemm_bf16(const missm_gemm_args* a, void* stream_v) {
   const long tiles = static_cast<long>(p.num_m_blk) * p.num_n_blk;
   int splits = 1;
   const bool may_split = (epi == MISSM_EPI_LINEAR && a->out_f32 && a->bias == nullptr &&
-                          a->scale_cols == 0 && a->split_k != 1);
+                          a->scale_cols == 0 && a->split_k != 1 && a->colsum_out == nullptr);
   if (may_split) {
     if (a->split_k > 1) {
       splits = a->split_k;

@@ -79,7 +79,8 @@ layernorm_fwd_kernel(const float* __restrict__ x, long ldx, const int* __restric
 }
 
 // dx[row] = (dres ? dres[row] : 0) + rstd * (g - mean(g) - xhat * mean(g * xhat)),  g = dy*gamma
-// partial[blockIdx][0][:] = sum_rows dy * xhat ; partial[blockIdx][1][:] = sum_rows dy
+// partial[blockIdx][0][:] = sum_rows dy * xhat ; partial[blockIdx][1][:] = sum_rows dy ;
+// partial[blockIdx][2][:] = sum_rows dx
 template <int VEC, bool DY_BF16>
 __global__ void __launch_bounds__(kLnWarps * 32)
 layernorm_bwd_kernel(const void* __restrict__ dy, long lddy, const float* __restrict__ x, long ldx,
@@ -89,9 +90,9 @@ layernorm_bwd_kernel(const void* __restrict__ dy, long lddy, const float* __rest
                      __nv_bfloat16* __restrict__ dx_bf16, float* __restrict__ partial, int M) {
   constexpr int D = VEC * 128;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  float4 dg[VEC], db[VEC];
+  float4 dg[VEC], db[VEC], ds[VEC];
 #pragma unroll
-  for (int i = 0; i < VEC; ++i) dg[i] = db[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int i = 0; i < VEC; ++i) dg[i] = db[i] = ds[i] = make_float4(0.f, 0.f, 0.f, 0.f);
 
   for (int row = blockIdx.x * kLnWarps + warp; row < M; row += gridDim.x * kLnWarps) {
     const long xrow = row_index ? row_index[row] : row;
@@ -132,6 +133,7 @@ layernorm_bwd_kernel(const void* __restrict__ dy, long lddy, const float* __rest
         o.x += r.x, o.y += r.y, o.z += r.z, o.w += r.w;
       }
       reinterpret_cast<float4*>(dx + xrow * ldx)[lane + 32 * i] = o;
+      ds[i].x += o.x, ds[i].y += o.y, ds[i].z += o.z, ds[i].w += o.w;
       if (dx_bf16 != nullptr)
         reinterpret_cast<uint2*>(dx_bf16 + xrow * ldx)[lane + 32 * i] =
             make_uint2(pack_bf16x2(o.x, o.y), pack_bf16x2(o.z, o.w));
@@ -140,12 +142,12 @@ layernorm_bwd_kernel(const void* __restrict__ dy, long lddy, const float* __rest
 
   // block reduction of the per-warp column sums through shared memory
   __shared__ float4 red[kLnWarps][32];
-  float* pg = partial + static_cast<long>(blockIdx.x) * 2 * D;
+  float* pg = partial + static_cast<long>(blockIdx.x) * 3 * D;
 #pragma unroll 1
-  for (int which = 0; which < 2; ++which) {
+  for (int which = 0; which < 3; ++which) {
 #pragma unroll 1
     for (int i = 0; i < VEC; ++i) {
-      red[warp][lane] = which == 0 ? dg[i] : db[i];
+      red[warp][lane] = which == 0 ? dg[i] : (which == 1 ? db[i] : ds[i]);
       __syncthreads();
       if (warp == 0) {
         float4 a = red[0][lane];
@@ -253,17 +255,18 @@ extern "C" int missm_layernorm_fwd(const float* x, int64_t ldx, const int32_t* r
                               x_out, gamma, beta, y, ldy, mean, rstd, M, eps);
 }
 
-// partial: workspace of missm_ln_bwd_num_partials(M) * 2 * D floats; dgamma/dbeta: [D] outputs.
+// partial: workspace of missm_ln_bwd_num_partials(M) * 3 * D floats; dgamma/dbeta/dx_colsum: [D].
 extern "C" int missm_layernorm_bwd(const void* dy, int64_t lddy, int32_t dy_bf16, const float* x,
                                    int64_t ldx, const int32_t* row_index, const float* mean,
                                    const float* rstd, const float* gamma, const float* dres,
                                    float* dx, void* dx_bf16, float* partial, float* dgamma,
-                                   float* dbeta, int32_t M, int32_t D, void* stream) {
+                                   float* dbeta, float* dx_colsum, int32_t M, int32_t D, void* stream) {
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   MISSM_REQUIRE(D % 128 == 0, "layernorm: D=%d", D);
   if (M == 0) {
     MISSM_CHECK_CUDA(cudaMemsetAsync(dgamma, 0, sizeof(float) * D, st));
     MISSM_CHECK_CUDA(cudaMemsetAsync(dbeta, 0, sizeof(float) * D, st));
+    if (dx_colsum) MISSM_CHECK_CUDA(cudaMemsetAsync(dx_colsum, 0, sizeof(float) * D, st));
     return 0;
   }
   const int grid = missm_ln_bwd_num_partials(M);
@@ -275,11 +278,14 @@ extern "C" int missm_layernorm_bwd(const void* dy, int64_t lddy, int32_t dy_bf16
     rc = launch_ln_bwd<false>(D / 128, grid, st, dy, lddy, x, ldx, row_index, mean, rstd, gamma,
                               dres, dx, static_cast<__nv_bfloat16*>(dx_bf16), partial, M);
   if (rc) return rc;
-  if (dbeta == dgamma + D) {  // contiguous [2, D] output: one launch
-    reduce_partials_kernel<<<(2 * D + 31) / 32, dim3(32, 8), 0, st>>>(partial, grid, 2L * D, dgamma, 2 * D, 1.f);
+  if (dbeta == dgamma + D && (dx_colsum == nullptr || dx_colsum == dbeta + D)) {  // contiguous output: one launch
+    const int n = (dx_colsum ? 3 : 2) * D;
+    reduce_partials_kernel<<<(n + 31) / 32, dim3(32, 8), 0, st>>>(partial, grid, 3L * D, dgamma, n, 1.f);
   } else {
-    reduce_partials_kernel<<<(D + 31) / 32, dim3(32, 8), 0, st>>>(partial, grid, 2L * D, dgamma, D, 1.f);
-    reduce_partials_kernel<<<(D + 31) / 32, dim3(32, 8), 0, st>>>(partial + D, grid, 2L * D, dbeta, D, 1.f);
+    reduce_partials_kernel<<<(D + 31) / 32, dim3(32, 8), 0, st>>>(partial, grid, 3L * D, dgamma, D, 1.f);
+    reduce_partials_kernel<<<(D + 31) / 32, dim3(32, 8), 0, st>>>(partial + D, grid, 3L * D, dbeta, D, 1.f);
+    if (dx_colsum)
+      reduce_partials_kernel<<<(D + 31) / 32, dim3(32, 8), 0, st>>>(partial + 2 * D, grid, 3L * D, dx_colsum, D, 1.f);
   }
   MISSM_CHECK_CUDA(cudaGetLastError());
   return 0;

@@ -14,7 +14,7 @@ SIGNATURES = {
     "missm_attention_bwd": [P, P],
     "missm_layernorm_fwd": [P, L, P, P, I, I, P, P, P, P, L, I, P, P, I, I, F, P],
     "missm_ln_bwd_num_partials": [I],
-    "missm_layernorm_bwd": [P, L, I, P, L, P, P, P, P, P, P, P, P, P, P, I, I, P],
+    "missm_layernorm_bwd": [P, L, I, P, L, P, P, P, P, P, P, P, P, P, P, P, I, I, P],
     "missm_reduce_partials": [P, I, L, P, I, F, P],
     "missm_cast_f32_bf16": [P, L, P, L, I, I, I, P],
     "missm_colsum_num_partials": [I],

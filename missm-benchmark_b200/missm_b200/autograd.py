@@ -5,6 +5,8 @@ Activations: fp32 residual stream [M, D]; bf16 GEMM operands; fp32 accumulation 
 Every Function returns an explicit gradient (never None) for every parameter it receives --
 DDP at train_ddp.py:189 runs with find_unused_parameters=False.
 """
+import os
+
 import torch
 
 from . import ops
@@ -17,16 +19,25 @@ from .ops import BF16, F32, EPI_DGELU, EPI_GELU, EPI_PATCH, EPI_RESID
 _GRAD_BF16 = {}
 
 
-def _publish_bf16(grad_f32, grad_bf16):
+_AB_NO_LN_COLSUM = os.environ.get("MISSM_AB_NO_LN_COLSUM") is not None     # A/B measurement switches
+_AB_DGELU_COLSUM = os.environ.get("MISSM_AB_DGELU_COLSUM") is not None
+
+
+def _publish_bf16(grad_f32, grad_bf16, colsum=None):
+    if _AB_NO_LN_COLSUM:
+        colsum = None
     # holding grad_f32 keeps its storage alive, so a pointer match means "the same tensor"
-    _GRAD_BF16[grad_f32.data_ptr()] = (grad_f32, grad_bf16)
+    _GRAD_BF16[grad_f32.data_ptr()] = (grad_f32, grad_bf16, colsum)
 
 
 def _bf16_of(grad_f32):
+    """-> (bf16 copy, column sums [D]) of a residual-stream gradient; both come for free from the
+    LayerNorm-backward kernel that produced it, else they are computed here."""
     hit = _GRAD_BF16.pop(grad_f32.data_ptr(), None)
     if hit is not None and hit[0].shape == grad_f32.shape and hit[0]._version == grad_f32._version:
-        return hit[1]
-    return ops.cast_bf16(grad_f32)
+        return hit[1], (hit[2] if hit[2] is not None else ops.colsum(hit[1]))
+    b = ops.cast_bf16(grad_f32)
+    return b, ops.colsum(b)
 
 
 def reset_side_channel():
@@ -116,17 +127,16 @@ class AttnBlockFn(torch.autograd.Function):
         D = x_res.shape[1]
         hd = D // meta.H
         d_out = _contig(d_out)
-        d_out_b = _bf16_of(d_out)
+        d_out_b, d_ob = _bf16_of(d_out)
         d_ow = ops.gemm(d_out_b, attn, a_mn=True, b_mn=True, out_dtype=F32)          # dY^T @ attn
-        d_ob = ops.colsum(d_out_b)
         d_attn = ops.gemm(d_out_b, wo, b_mn=True)                                      # dY @ Wo
         dqkv = ops.attention_bwd(qkv, attn, lse, d_attn, meta.layout, meta.H, hd ** -0.5, causal=meta.causal,
                                  key_mask=meta.key_mask, mask_rows=meta.mask_rows, mask_div=meta.mask_div)
         d_wqkv = ops.gemm(dqkv, h, a_mn=True, b_mn=True, out_dtype=F32)               # [3D, D]
         d_bqkv = ops.colsum(dqkv)
         d_h = ops.gemm(dqkv, wqkv, b_mn=True)
-        dx, dx_b, d_lnw, d_lnb = ops.layernorm_bwd(d_h, x_res, mean, rstd, ln_w, dres=d_out, want_bf16=True)
-        _publish_bf16(dx, dx_b)
+        dx, dx_b, d_lnw, d_lnb, dx_cs = ops.layernorm_bwd(d_h, x_res, mean, rstd, ln_w, dres=d_out, want_bf16=True)
+        _publish_bf16(dx, dx_b, dx_cs)
         d_temb = None
         if ctx.has_temb:
             d_temb = ops.colsum_grouped(dx, meta.add_period, meta.add_div).view(1, meta.add_period, D)
@@ -153,15 +163,21 @@ class MlpBlockFn(torch.autograd.Function):
     def backward(ctx, d_out):
         x, mean, rstd, h, u, a, w1b, w2b, ln_w = ctx.saved_tensors
         d_out = _contig(d_out)
-        d_out_b = _bf16_of(d_out)
+        d_out_b, d_b2 = _bf16_of(d_out)
         d_w2 = ops.gemm(d_out_b, a, a_mn=True, b_mn=True, out_dtype=F32)
-        d_b2 = ops.colsum(d_out_b)
-        d_u = ops.gemm(d_out_b, w2b, b_mn=True, epilogue=EPI_DGELU, aux_in=u)         # (dY @ W2) * gelu'(u)
+        if _AB_DGELU_COLSUM:
+            d_b1 = torch.zeros((u.shape[1],), device=u.device, dtype=F32)
+            d_u = ops.gemm(d_out_b, w2b, b_mn=True, epilogue=EPI_DGELU, aux_in=u, colsum_out=d_b1)
+        else:
+            d_u = ops.gemm(d_out_b, w2b, b_mn=True, epilogue=EPI_DGELU, aux_in=u)     # (dY @ W2) * gelu'(u)
         d_w1 = ops.gemm(d_u, h, a_mn=True, b_mn=True, out_dtype=F32)
-        d_b1 = ops.colsum(d_u)
+        # (the GEMM can also emit this column sum -- colsum_out -- but the dGELU epilogue is already the
+        #  bound of that kernel: measured 3 ms / step slower than this separate HBM-bound pass)
+        if not _AB_DGELU_COLSUM:
+            d_b1 = ops.colsum(d_u)
         d_h = ops.gemm(d_u, w1b, b_mn=True)
-        dx, dx_b, d_lnw, d_lnb = ops.layernorm_bwd(d_h, x, mean, rstd, ln_w, dres=d_out, want_bf16=True)
-        _publish_bf16(dx, dx_b)
+        dx, dx_b, d_lnw, d_lnb, dx_cs = ops.layernorm_bwd(d_h, x, mean, rstd, ln_w, dres=d_out, want_bf16=True)
+        _publish_bf16(dx, dx_b, dx_cs)
         return dx, None, None, d_lnw, d_lnb, d_w1, d_b1, d_w2, d_b2
 
 
@@ -195,7 +211,7 @@ class VisionEmbedFn(torch.autograd.Function):
         n_img, P, D, K, wshape = ctx.dims
         d_x0 = _contig(d_x0)
         _GRAD_BF16.pop(d_x0.data_ptr(), None)
-        d_tok, _, d_lnw, d_lnb = ops.layernorm_bwd(d_x0, tok, mean, rstd, ln_w)
+        d_tok, _, d_lnw, d_lnb, _ = ops.layernorm_bwd(d_x0, tok, mean, rstd, ln_w)
         d_pos, d_patch = ops.embed_bwd(d_tok, n_img, P + 1)
         d_w = ops.gemm(d_patch, patches, a_mn=True, b_mn=True, out_dtype=F32)          # [D, Kpad]
         d_w = d_w[:, :K].reshape(wshape)
@@ -267,9 +283,9 @@ class PoolProjFn(torch.autograd.Function):
             d_pooled = ops.frame_mean_bwd(d_pm, n_present, T)                          # f32 [Bp*T, D]
         dx = torch.zeros_like(x)
         dx_b = torch.zeros(x.shape, device=x.device, dtype=BF16)
-        _, _, d_lnw, d_lnb = ops.layernorm_bwd(d_pooled, x, mean, rstd, ln_w, row_index=rows, dx=dx,
-                                                dx_bf16=dx_b)
-        _publish_bf16(dx, dx_b)
+        _, _, d_lnw, d_lnb, dx_cs = ops.layernorm_bwd(d_pooled, x, mean, rstd, ln_w, row_index=rows, dx=dx,
+                                                       dx_bf16=dx_b)
+        _publish_bf16(dx, dx_b, dx_cs)
         return dx, None, None, None, None, None, None, d_lnw, d_lnb, d_proj
 
 

@@ -31,9 +31,10 @@ def _ld(t):
 # --------------------------------------------------------------------------------------- GEMM
 def gemm(a, b, *, a_mn=False, b_mn=False, out=None, out_dtype=BF16, bias=None,
          epilogue=EPI_LINEAR, aux_in=None, aux_out=None, scale_cols=0, col_scale=1.0,
-         patch_P=0, out_rows=None, split_k=0, force_bn=0):
+         patch_P=0, out_rows=None, split_k=0, force_bn=0, colsum_out=None):
     """C[m,n] = epilogue(sum_k A[m,k] B[n,k]).  `a`: [M,K] (or [K,M] if a_mn), `b`: [N,K]
-    (or [K,N] if b_mn); both bf16 CUDA tensors, row-major."""
+    (or [K,N] if b_mn); both bf16 CUDA tensors, row-major.  `colsum_out` (f32 [N], pre-zeroed) receives
+    the column sums of the fp32 values written to C (fused bias gradient)."""
     assert a.is_cuda and b.is_cuda and a.dtype == BF16 and b.dtype == BF16
     M, K = (a.shape[1], a.shape[0]) if a_mn else (a.shape[0], a.shape[1])
     N, Kb = (b.shape[1], b.shape[0]) if b_mn else (b.shape[0], b.shape[1])
@@ -58,6 +59,9 @@ def gemm(a, b, *, a_mn=False, b_mn=False, out=None, out_dtype=BF16, bias=None,
     g.out_f32 = int(out.dtype == F32)
     g.scale_cols, g.col_scale = scale_cols, col_scale
     g.patch_P, g.split_k, g.force_bn = patch_P, split_k, force_bn
+    if colsum_out is not None:
+        assert colsum_out.dtype == F32 and colsum_out.numel() == N and colsum_out.is_contiguous()
+        g.colsum_out = colsum_out.data_ptr()
     LAUNCHES[0] += 1
     if GEMM_TIMING is not None and M > 0:
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -154,8 +158,9 @@ def layernorm_fwd(x, gamma, beta, eps, *, out_dtype=BF16, row_index=None, n_rows
 
 def layernorm_bwd(dy, x, mean, rstd, gamma, *, dres=None, row_index=None, dx=None,
                   want_bf16=False, dx_bf16=None):
-    """-> (dx f32 like x, dx_bf16 or None, dgamma [D], dbeta [D]).  With row_index, dx must be a
-    pre-zeroed full-size tensor and only the indexed rows are written."""
+    """-> (dx f32 like x, dx_bf16 or None, dgamma [D], dbeta [D], dx_colsum [D]).  With row_index, dx
+    must be a pre-zeroed full-size tensor and only the indexed rows are written.  dx_colsum = column
+    sums of the written rows of dx: the bias gradient of the Linear whose output this stream is."""
     D = x.shape[1]
     M = dy.shape[0]
     if dx is None:
@@ -164,15 +169,15 @@ def layernorm_bwd(dy, x, mean, rstd, gamma, *, dres=None, row_index=None, dx=Non
     if want_bf16 and dx_bf16 is None:
         dx_bf16 = torch.empty(x.shape, device=x.device, dtype=BF16)
     nparts = lib().missm_ln_bwd_num_partials(M)
-    partial = torch.empty((nparts, 2, D), device=x.device, dtype=F32)
-    dgb = torch.empty((2, D), device=x.device, dtype=F32)
-    dgamma, dbeta = dgb[0], dgb[1]
+    partial = torch.empty((nparts, 3, D), device=x.device, dtype=F32)
+    dgb = torch.empty((3, D), device=x.device, dtype=F32)
+    dgamma, dbeta, dcol = dgb[0], dgb[1], dgb[2]
     LAUNCHES[0] += 2
     check(lib().missm_layernorm_bwd(_p(dy), _ld(dy), int(dy.dtype == BF16), _p(x), _ld(x),
                                     _p(row_index), _p(mean), _p(rstd), _p(gamma), _p(dres), _p(dx),
-                                    _p(dx_bf16), _p(partial), _p(dgamma), _p(dbeta), M, D,
+                                    _p(dx_bf16), _p(partial), _p(dgamma), _p(dbeta), _p(dcol), M, D,
                                     stream_ptr()), "layernorm_bwd")
-    return dx, dx_bf16, dgamma, dbeta
+    return dx, dx_bf16, dgamma, dbeta, dcol
 
 
 # ------------------------------------------------------------------------------------ helpers

@@ -38,9 +38,10 @@ def test_gemm_layouts(ops, a_mn, b_mn, shape):
         assert rel(out, ref) < 1e-5
 
 
-def test_gemm_epilogues(ops):
+@pytest.mark.parametrize("M", [700, 1500])       # 700: one-CTA kernel; 1500: CTA-pair (cta_group::2) kernel
+def test_gemm_epilogues(ops, M):
     torch.manual_seed(1)
-    M, N, K = 700, 1024, 512
+    N, K = 1024, 512
     A = torch.randn(M, K, device=DEV).bfloat16()
     B = (torch.randn(N, K, device=DEV) * 0.05).bfloat16()
     bias = torch.randn(N, device=DEV)
@@ -59,10 +60,15 @@ def test_gemm_epilogues(ops):
     ops.gemm(A, B, bias=bias, epilogue=ops.EPI_RESID, aux_in=res2, out=res2)
     assert rel(res2, res + pre) < 1e-5
     uu = torch.randn(M, N, device=DEV).bfloat16()
-    out = ops.gemm(A, B, epilogue=ops.EPI_DGELU, aux_in=uu)
+    cs = torch.zeros(N, device=DEV)
+    out = ops.gemm(A, B, epilogue=ops.EPI_DGELU, aux_in=uu, colsum_out=cs)
     s = torch.sigmoid(1.702 * uu.float())
-    assert rel(out, acc * (s * (1 + 1.702 * uu.float() * (1 - s)))) < 4e-3
-    P, Bsz = 100, 7
+    dref = acc * (s * (1 + 1.702 * uu.float() * (1 - s)))
+    assert rel(out, dref) < 4e-3
+    assert rel(cs, dref.sum(0)) < 2e-5              # fused bias gradient (fp32 values, before the bf16 rounding)
+    P = 100
+    Bsz = M // P
+    A, acc = A[:Bsz * P], acc[:Bsz * P]
     pos = torch.randn(P + 1, N, device=DEV)
     tok = torch.zeros(Bsz * (P + 1), N, device=DEV)
     ops.gemm(A, B, epilogue=ops.EPI_PATCH, aux_in=pos, out=tok, patch_P=P)
@@ -101,12 +107,13 @@ def test_layernorm_fwd_bwd(ops, D):
     dy = torch.randn(M, D, device=DEV)
     dres = torch.randn(M, D, device=DEV)
     ref.backward(dy)
-    dx, dxb, dg, db = ops.layernorm_bwd(dy, x.detach(), mean, rstd, g.detach(), dres=dres, want_bf16=True)
+    dx, dxb, dg, db, dcs = ops.layernorm_bwd(dy, x.detach(), mean, rstd, g.detach(), dres=dres, want_bf16=True)
     assert rel(dx, x.grad + dres) < 1e-5
+    assert rel(dcs, (x.grad + dres).sum(0)) < 1e-5          # fused column sums (bias gradient of the producer)
     assert rel(dxb, x.grad + dres) < 4e-3
     assert rel(dg, g.grad) < 1e-5 and rel(db, b.grad) < 1e-5
     # bf16 dy
-    dx2, _, dg2, _ = ops.layernorm_bwd(dy.bfloat16(), x.detach(), mean, rstd, g.detach())
+    dx2, _, dg2, _, _ = ops.layernorm_bwd(dy.bfloat16(), x.detach(), mean, rstd, g.detach())
     x.grad = None; g.grad = None
     torch.nn.functional.layer_norm(x, (D,), g, b, 1e-5).backward(dy.bfloat16().float())
     assert rel(dx2, x.grad) < 1e-5 and rel(dg2, g.grad) < 1e-5
@@ -123,10 +130,11 @@ def test_layernorm_gather_and_add(ops):
     assert rel(y, ref) < 1e-6
     dy = torch.randn(B * T, D, device=DEV)
     dx = torch.zeros_like(x)
-    ops.layernorm_bwd(dy, x, mean, rstd, g, row_index=rows, dx=dx)
+    dcs = ops.layernorm_bwd(dy, x, mean, rstd, g, row_index=rows, dx=dx)[4]
     xr = x.clone().requires_grad_(True)
     torch.nn.functional.layer_norm(xr[rows.long()], (D,), g, b, 1e-5).backward(dy)
     assert rel(dx, xr.grad) < 1e-5
+    assert rel(dcs, xr.grad.sum(0)) < 1e-5
     # temporal embedding add: x <- x + temb[(row // N) % T]
     temb = torch.randn(T, D, device=DEV)
     x2 = x.clone()
