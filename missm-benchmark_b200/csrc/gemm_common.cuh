@@ -86,28 +86,29 @@ __device__ __forceinline__ void tile_ldg(const void* base, long ld, int col0, in
   }
 }
 template <bool F32>
-__device__ __forceinline__ void tile_sts(uint8_t* stage, int lane, const uint4 (&val)[8]) {
+__device__ __forceinline__ void tile_sts(uint32_t stage, int lane, const uint4 (&val)[8]) {
   constexpr int CH = F32 ? 8 : 4, RPI = 32 / CH, NI = 32 / RPI;
   const int c = lane % CH;
 #pragma unroll
   for (int i = 0; i < NI; ++i) {
     const int r = i * RPI + lane / CH;
-    *reinterpret_cast<uint4*>(stage + stage_off(r, c)) = val[i];
+    sts128(stage + stage_off(r, c), val[i]);
   }
 }
 // staging -> this thread's row as 32 floats
 template <bool F32>
-__device__ __forceinline__ void tile_row_read(const uint8_t* stage, int lane, float (&x)[32]) {
+__device__ __forceinline__ void tile_row_read(uint32_t stage, int lane, float (&x)[32]) {
   if constexpr (F32) {
 #pragma unroll
     for (int c = 0; c < 8; ++c) {
-      const float4 v = *reinterpret_cast<const float4*>(stage + stage_off(lane, c));
-      x[4 * c] = v.x, x[4 * c + 1] = v.y, x[4 * c + 2] = v.z, x[4 * c + 3] = v.w;
+      const uint4 v = lds128(stage + stage_off(lane, c));
+      x[4 * c] = __uint_as_float(v.x), x[4 * c + 1] = __uint_as_float(v.y);
+      x[4 * c + 2] = __uint_as_float(v.z), x[4 * c + 3] = __uint_as_float(v.w);
     }
   } else {
 #pragma unroll
     for (int c = 0; c < 4; ++c) {
-      const uint4 q = *reinterpret_cast<const uint4*>(stage + stage_off(lane, c));
+      const uint4 q = lds128(stage + stage_off(lane, c));
       const float2 a = unpack_bf16x2(q.x), b = unpack_bf16x2(q.y), d = unpack_bf16x2(q.z), e = unpack_bf16x2(q.w);
       x[8 * c] = a.x, x[8 * c + 1] = a.y, x[8 * c + 2] = b.x, x[8 * c + 3] = b.y;
       x[8 * c + 4] = d.x, x[8 * c + 5] = d.y, x[8 * c + 6] = e.x, x[8 * c + 7] = e.y;
@@ -116,24 +117,25 @@ __device__ __forceinline__ void tile_row_read(const uint8_t* stage, int lane, fl
 }
 // this thread's row (32 floats) -> staging as fp32 or bf16
 template <bool F32>
-__device__ __forceinline__ void tile_row_write(uint8_t* stage, int lane, const float (&x)[32]) {
+__device__ __forceinline__ void tile_row_write(uint32_t stage, int lane, const float (&x)[32]) {
   if constexpr (F32) {
 #pragma unroll
     for (int c = 0; c < 8; ++c)
-      *reinterpret_cast<float4*>(stage + stage_off(lane, c)) = make_float4(x[4 * c], x[4 * c + 1], x[4 * c + 2], x[4 * c + 3]);
+      sts128(stage + stage_off(lane, c), make_uint4(__float_as_uint(x[4 * c]), __float_as_uint(x[4 * c + 1]),
+                                                    __float_as_uint(x[4 * c + 2]), __float_as_uint(x[4 * c + 3])));
   } else {
 #pragma unroll
     for (int c = 0; c < 4; ++c) {
       uint4 q;
       q.x = pack_bf16x2(x[8 * c], x[8 * c + 1]), q.y = pack_bf16x2(x[8 * c + 2], x[8 * c + 3]);
       q.z = pack_bf16x2(x[8 * c + 4], x[8 * c + 5]), q.w = pack_bf16x2(x[8 * c + 6], x[8 * c + 7]);
-      *reinterpret_cast<uint4*>(stage + stage_off(lane, c)) = q;
+      sts128(stage + stage_off(lane, c), q);
     }
   }
 }
 // staging -> global, coalesced; `atomic` (fp32 only): red.global.add instead of a store
 template <bool F32, typename RowMap>
-__device__ __forceinline__ void tile_stg(void* base, long ld, int col0, int ncols, const RowMap& rm, const uint8_t* stage,
+__device__ __forceinline__ void tile_stg(void* base, long ld, int col0, int ncols, const RowMap& rm, uint32_t stage,
                                          int lane, bool atomic) {
   constexpr int CH = F32 ? 8 : 4, RPI = 32 / CH, EPC = F32 ? 4 : 8, NI = 32 / RPI, ES = F32 ? 4 : 2;
   const int c = lane % CH;
@@ -142,7 +144,7 @@ __device__ __forceinline__ void tile_stg(void* base, long ld, int col0, int ncol
     const int r = i * RPI + lane / CH;
     const long g = rm(r);
     if (g >= 0 && c * EPC < ncols) {
-      const uint4 v = *reinterpret_cast<const uint4*>(stage + stage_off(r, c));
+      const uint4 v = lds128(stage + stage_off(r, c));
       char* dst = static_cast<char*>(base) + (g * ld + col0 + c * EPC) * ES;
       if (F32 && atomic) {
         asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst), "f"(__uint_as_float(v.x)),
@@ -173,21 +175,29 @@ __device__ __forceinline__ float warp_colsum32(float (&v)[32], int lane) {
 
 // `row0`: global row of this warp's lane 0; `acc`: this thread's row (row0 + lane) of the fp32
 // accumulator, columns [col0, col0 + 32).  All 32 lanes must call (warp-collective).
+// The auxiliary input tile of a chunk (residual / pre-activation / position rows), as coalesced
+// global loads into registers.  Issued one chunk AHEAD of its use (the epilogue warps have no other
+// way to hide a global-memory round trip: two warps per scheduler, one chunk at a time).
+template <int EPI>
+__device__ __forceinline__ void epilogue_aux_load(const GemmParams& p, int row0, int col0, int lane, uint4 (&aux)[8]) {
+  if (row0 >= p.M || col0 >= p.N) return;
+  const int ncols = min(32, p.N - col0);
+  if constexpr (EPI == MISSM_EPI_RESID) tile_ldg<true>(p.aux_in, p.ld_aux_in, col0, ncols, RowMapIdentity{row0, p.M}, lane, aux);
+  if constexpr (EPI == MISSM_EPI_DGELU) tile_ldg<false>(p.aux_in, p.ld_aux_in, col0, ncols, RowMapIdentity{row0, p.M}, lane, aux);
+  if constexpr (EPI == MISSM_EPI_PATCH)
+    tile_ldg<true>(p.aux_in, p.ld_aux_in, col0, ncols, RowMapPatchPos{row0, p.M, p.patch_P}, lane, aux);
+}
+template <int EPI>
+constexpr bool epilogue_has_aux() { return EPI == MISSM_EPI_RESID || EPI == MISSM_EPI_DGELU || EPI == MISSM_EPI_PATCH; }
+
 template <int EPI, bool OUT_F32>
 __device__ __forceinline__ void epilogue_chunk(const GemmParams& p, int row0, int col0, const uint32_t (&acc)[32],
-                                               uint8_t* stage, int lane) {
+                                               const uint4 (&aux)[8], uint32_t stage, int lane) {
   const int ncols = min(32, p.N - col0);  // N % 8 == 0 is enforced by the host
   const RowMapIdentity rows{row0, p.M};
   float v[32];
 #pragma unroll
   for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(acc[j]);
-
-  // ---- auxiliary input tile (issued first: its latency overlaps the bias math)
-  uint4 aux[8];
-  if constexpr (EPI == MISSM_EPI_RESID) tile_ldg<true>(p.aux_in, p.ld_aux_in, col0, ncols, rows, lane, aux);
-  if constexpr (EPI == MISSM_EPI_DGELU) tile_ldg<false>(p.aux_in, p.ld_aux_in, col0, ncols, rows, lane, aux);
-  if constexpr (EPI == MISSM_EPI_PATCH)
-    tile_ldg<true>(p.aux_in, p.ld_aux_in, col0, ncols, RowMapPatchPos{row0, p.M, p.patch_P}, lane, aux);
 
   if (p.bias != nullptr) {
 #pragma unroll

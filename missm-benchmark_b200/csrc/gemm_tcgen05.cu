@@ -86,7 +86,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA,
       uint32_t phase = 0;
       for (int w = blockIdx.x; w < total_work; w += gridDim.x) {
         const int split = w / tiles_mn, rem = w % tiles_mn;
-        const int n_blk = rem / p.num_m_blk, m_blk = rem % p.num_m_blk;
+        const int m_blk = rem / p.num_n_blk, n_blk = rem % p.num_n_blk;
         const int kb0 = split * p.kblk_per_split;
         const int kb1 = min(kb0 + p.kblk_per_split, p.num_kblk);
         for (int kb = kb0; kb < kb1; ++kb) {
@@ -163,15 +163,19 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA,
     // ================================ epilogue ========================================
     const int q = warp & 3;               // TMEM lane quarter this warp may access
     const int half = (warp - 4) >> 2;     // the two warps of a quarter split the column chunks
-    uint8_t* stage = sStage + (warp - 4) * kEpiStageBytes;
+    const uint32_t stage = smem_u32(sStage) + (warp - 4) * kEpiStageBytes;   // shared-space address
     int acc = 0;
     uint32_t acc_phase = 0;
     for (int w = blockIdx.x; w < total_work; w += gridDim.x) {
       const int rem = w % tiles_mn;
-      const int n_blk = rem / p.num_m_blk, m_blk = rem % p.num_m_blk;
+      const int m_blk = rem / p.num_n_blk, n_blk = rem % p.num_n_blk;
+      const int row0 = m_blk * BM + q * 32;
+      // in-place RESID (aux_in aliases C): this warp's tile is only ever touched by this warp, and its
+      // loads are issued before its stores
+      uint4 aux[8], aux_next[8];
+      if constexpr (epilogue_has_aux<EPI>()) epilogue_aux_load<EPI>(p, row0, n_blk * BN + half * 32, lane, aux);
       mbar_wait(&tfull_bar[acc], acc_phase);
       tc_fence_after();
-      const int row0 = m_blk * BM + q * 32;
       const uint32_t t_row = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * BN;
 #pragma unroll 1
       for (int c = half; c < BN / 32; c += kEpiWarps / 4) {
@@ -179,8 +183,15 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA,
         if (col0 >= p.N) break;  // warp-uniform
         uint32_t r[32];
         tmem_ld_32x32b_x32(t_row + c * 32, r);
+        if constexpr (epilogue_has_aux<EPI>()) {
+          if (c + kEpiWarps / 4 < BN / 32) epilogue_aux_load<EPI>(p, row0, col0 + (kEpiWarps / 4) * 32, lane, aux_next);
+        }
         tmem_ld_wait();
-        if (row0 < p.M) epilogue_chunk<EPI, OUT_F32>(p, row0, col0, r, stage, lane);   // warp-uniform
+        if (row0 < p.M) epilogue_chunk<EPI, OUT_F32>(p, row0, col0, r, aux, stage, lane);   // warp-uniform
+        if constexpr (epilogue_has_aux<EPI>()) {
+#pragma unroll
+          for (int i = 0; i < 8; ++i) aux[i] = aux_next[i];
+        }
       }
       tc_fence_before();
       __syncwarp();

@@ -39,6 +39,18 @@ __device__ __forceinline__ uint32_t smem_u32(const void* p) {
   return static_cast<uint32_t>(__cvta_generic_to_shared(p));
 }
 __device__ __forceinline__ int lane_id() { return threadIdx.x & 31; }
+// Explicit shared-space 128-bit accesses.  Pointers carved out of the dynamic shared buffer through
+// integer arithmetic lose their address space, and ptxas then emits GENERIC LD/ST (plus a heavier
+// fence at every __syncwarp) -- measured 2-3x slower epilogues; these keep LDS/STS.
+__device__ __forceinline__ uint4 lds128(uint32_t saddr) {
+  uint4 v;
+  asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(saddr));
+  return v;
+}
+__device__ __forceinline__ void sts128(uint32_t saddr, const uint4& v) {
+  asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(saddr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w)
+               : "memory");
+}
 // One lane of a CONVERGED warp.  Single-thread work (tcgen05.mma / TMA issue) is written as
 // `if (elect_one_sync()) {...}` inside warp-uniform code rather than under `if (lane == 0)`: only
 // then does ptxas keep descriptors and TMEM addresses in uniform registers instead of wrapping every
@@ -290,7 +302,10 @@ __device__ __forceinline__ uint32_t mapa_shared(uint32_t saddr, uint32_t rank) {
   return r;
 }
 __device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
-  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+  // default semantics (.release at CTA scope), as CUTLASS' ClusterBarrier::arrive(cta_id): an explicit
+  // .release.cluster makes ptxas emit MEMBAR.ALL.GPU, which stalls the epilogue warp until all of its
+  // global stores have drained -- the barrier only has to order this warp's TMEM reads (tcgen05 fence)
+  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
 }
 __device__ __forceinline__ void tmem_alloc_2cta(uint32_t* smem_dst, uint32_t ncols) {
   asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(smem_dst)),
