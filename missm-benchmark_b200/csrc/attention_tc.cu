@@ -68,7 +68,8 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm128, const __grid_const
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
   uint8_t* sKV = smem;                              // [item buffer][K | V]: 2 x 2 x 34 KB
   uint8_t* sQ = sKV + 4 * FW_KV_BYTES;              // 2 x 16 KB
-  AttnFwdSmem* sh = reinterpret_cast<AttnFwdSmem*>(sQ + 2 * FW_TILE_BYTES);
+  uint8_t* sStage = sQ + 2 * FW_TILE_BYTES;           // 8 softmax warps x 2 KB output staging
+  AttnFwdSmem* sh = reinterpret_cast<AttnFwdSmem*>(sStage + 8 * 2048);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
@@ -197,6 +198,7 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm128, const __grid_const
     const uint32_t p_addr = tmem + lane_addr + FW_P_COL;
     uint32_t tr = 0;
     const bool tracer = (q == 0 && lane == 0);
+    const uint32_t stage = smem_u32(sStage) + (warp - 4) * 2048;
 
     // epilogue of a finished tile: O / l -> bf16 (this warp writes columns [g*32, g*32+32)), lse
     auto epilogue = [&](uint32_t tc, int item, int tile, float mx, float sum_own, bool has_rows) {
@@ -212,20 +214,16 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm128, const __grid_const
       tc_fence_before();
       mbar_arrive(&sh->o_empty);
       const int row = tile * 128 + rloc;
-      if (has_rows && row < p.N) {
+      if (has_rows) {     // warp-uniform
         const int s = item / p.H, h = item % p.H;
         const float inv = 1.0f / sum;
-        uint4* dst = reinterpret_cast<uint4*>(p.out + (static_cast<long>(s) * p.N + row) * p.ld_o + h * 64 + g * 32);
+        float v[32];
 #pragma unroll
-        for (int j = 0; j < 32; j += 8) {
-          uint4 v;
-          v.x = pack_bf16x2(__uint_as_float(o[j]) * inv, __uint_as_float(o[j + 1]) * inv);
-          v.y = pack_bf16x2(__uint_as_float(o[j + 2]) * inv, __uint_as_float(o[j + 3]) * inv);
-          v.z = pack_bf16x2(__uint_as_float(o[j + 4]) * inv, __uint_as_float(o[j + 5]) * inv);
-          v.w = pack_bf16x2(__uint_as_float(o[j + 6]) * inv, __uint_as_float(o[j + 7]) * inv);
-          dst[j >> 3] = v;
-        }
-        if (g == 0 && p.lse != nullptr) p.lse[static_cast<long>(item) * p.N + row] = mx + __logf(sum);
+        for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(o[j]) * inv;
+        const int wrow0 = tile * 128 + q * 32;
+        warp_store_tile32_bf16(stage, lane, v, p.out + (static_cast<long>(s) * p.N + wrow0) * p.ld_o + h * 64 + g * 32,
+                               p.ld_o, p.N - wrow0);
+        if (row < p.N && g == 0 && p.lse != nullptr) p.lse[static_cast<long>(item) * p.N + row] = mx + __logf(sum);
       }
       if (tracer) fw_trace(p, 1 + g, tr, 14, tc);
     };
@@ -353,7 +351,7 @@ int attention_fwd_tc(const missm_attn_args* a, cudaStream_t stream) {
   p.nt = (a->N + 127) / 128;
   p.out = static_cast<__nv_bfloat16*>(a->out), p.ld_o = a->ld_o, p.lse = a->lse;
   p.trace = nullptr;
-  const int smem = 4 * FW_KV_BYTES + 2 * FW_TILE_BYTES + static_cast<int>(sizeof(AttnFwdSmem)) + 1024;
+  const int smem = 4 * FW_KV_BYTES + 2 * FW_TILE_BYTES + 8 * 2048 + static_cast<int>(sizeof(AttnFwdSmem)) + 1024;
   static bool configured = false;
   if (!configured) {
     MISSM_CHECK_CUDA(cudaFuncSetAttribute(attn_fwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));

@@ -145,27 +145,16 @@ __device__ __forceinline__ void bwd_chunk(uint32_t t_s, uint32_t t_dp, uint32_t 
   }
 }
 
-__device__ __forceinline__ void store_row64_bf16(__nv_bfloat16* dst, const uint32_t (&a)[32],
-                                                 const uint32_t (&b)[32], float scale) {
-  uint4* d4 = reinterpret_cast<uint4*>(dst);
+// accumulator rows (one per thread, 64 fp32 columns in two 32-column register blocks) -> bf16 -> HBM
+__device__ __forceinline__ void store_rows64_bf16(uint32_t stage, int lane, const uint32_t (&a)[32], const uint32_t (&b)[32],
+                                                  float scale, __nv_bfloat16* g, long ld, int nrows) {
+  float v[32];
 #pragma unroll
-  for (int j = 0; j < 32; j += 8) {
-    uint4 v;
-    v.x = pack_bf16x2(__uint_as_float(a[j]) * scale, __uint_as_float(a[j + 1]) * scale);
-    v.y = pack_bf16x2(__uint_as_float(a[j + 2]) * scale, __uint_as_float(a[j + 3]) * scale);
-    v.z = pack_bf16x2(__uint_as_float(a[j + 4]) * scale, __uint_as_float(a[j + 5]) * scale);
-    v.w = pack_bf16x2(__uint_as_float(a[j + 6]) * scale, __uint_as_float(a[j + 7]) * scale);
-    d4[j >> 3] = v;
-  }
+  for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(a[j]) * scale;
+  warp_store_tile32_bf16(stage, lane, v, g, ld, nrows);
 #pragma unroll
-  for (int j = 0; j < 32; j += 8) {
-    uint4 v;
-    v.x = pack_bf16x2(__uint_as_float(b[j]) * scale, __uint_as_float(b[j + 1]) * scale);
-    v.y = pack_bf16x2(__uint_as_float(b[j + 2]) * scale, __uint_as_float(b[j + 3]) * scale);
-    v.z = pack_bf16x2(__uint_as_float(b[j + 4]) * scale, __uint_as_float(b[j + 5]) * scale);
-    v.w = pack_bf16x2(__uint_as_float(b[j + 6]) * scale, __uint_as_float(b[j + 7]) * scale);
-    d4[4 + (j >> 3)] = v;
-  }
+  for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(b[j]) * scale;
+  warp_store_tile32_bf16(stage, lane, v, g + 32, ld, nrows);
 }
 
 // tm128 / tm16: [3D cols, N rows, n_seq] views of qkv with 64 x 128 and 64 x 16 boxes; td128 / td16:
@@ -181,7 +170,8 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm128, const __grid_const
   uint8_t* sRes = smem;                                   // 2 x 2 x 34 KB
   uint8_t* sTile = sRes + 4 * BW_RES_BYTES;               // [tile buffer][operand]: 2 x 2 x 16 KB
   float* sStat = reinterpret_cast<float*>(sTile + 4 * BW_TILE_BYTES);   // [item buffer][nlse2 | delta][BW_STAT]
-  AttnBwdSmem* sh = reinterpret_cast<AttnBwdSmem*>(sStat + 4 * BW_STAT);
+  uint8_t* sStage = reinterpret_cast<uint8_t*>(sStat + 4 * BW_STAT);    // 8 softmax warps x 2 KB output staging
+  AttnBwdSmem* sh = reinterpret_cast<AttnBwdSmem*>(sStage + 8 * 2048);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   constexpr int NACC = DKV ? 1 : 2;   // DKV: dV | dK fill the 128 accumulator columns; DQ: dQ double-buffered
@@ -380,6 +370,7 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm128, const __grid_const
     int stats_tile = -1, pre_tile = -1;
     uint32_t tr = 0;
     const bool tracer = (q == 0 && lane == 0);
+    const uint32_t stage = smem_u32(sStage) + (warp - 4) * 2048;
     BwCursor c;
     c.init();
     while (c.valid(p)) {
@@ -437,21 +428,23 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm128, const __grid_const
           tc_fence_after();
           if (tracer) bw_trace(p, 1 + g, tr, 13, c.n);
           const int s = c.item / p.H, h = c.item % p.H;
-          __nv_bfloat16* grow = p.dqkv + (static_cast<long>(s) * p.N + row) * p.ld_qkv + h * 64;
+          const int wrow0 = c.tile * 128 + q * 32;            // first row of this warp
+          __nv_bfloat16* grow = p.dqkv + (static_cast<long>(s) * p.N + wrow0) * p.ld_qkv + h * 64;
+          const int nrows = p.N - wrow0;
           if constexpr (DKV) {
             uint32_t x0[32], x1[32];
             if (warp_has_rows) {
               tmem_ld_32x32b_x32(tmem + lane_addr + BW_ACC_COL, x0);
               tmem_ld_32x32b_x32(tmem + lane_addr + BW_ACC_COL + 32, x1);
               tmem_ld_wait();
-              if (row < p.N) store_row64_bf16(grow + 2 * p.D, x0, x1, 1.0f);     // dV
+              store_rows64_bf16(stage, lane, x0, x1, 1.0f, grow + 2 * p.D, p.ld_qkv, nrows);     // dV
               tmem_ld_32x32b_x32(tmem + lane_addr + BW_ACC_COL + 64, x0);
               tmem_ld_32x32b_x32(tmem + lane_addr + BW_ACC_COL + 96, x1);
               tmem_ld_wait();
             }
             tc_fence_before();
             mbar_arrive(&sh->acc_empty[acc]);
-            if (warp_has_rows && row < p.N) store_row64_bf16(grow + p.D, x0, x1, 1.0f);   // dK
+            if (warp_has_rows) store_rows64_bf16(stage, lane, x0, x1, 1.0f, grow + p.D, p.ld_qkv, nrows);   // dK
           } else {
             uint32_t x0[32], x1[32];
             if (warp_has_rows) {
@@ -461,7 +454,7 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm128, const __grid_const
             }
             tc_fence_before();
             mbar_arrive(&sh->acc_empty[acc]);
-            if (warp_has_rows && row < p.N) store_row64_bf16(grow, x0, x1, p.q_scale);    // dQ
+            if (warp_has_rows) store_rows64_bf16(stage, lane, x0, x1, p.q_scale, grow, p.ld_qkv, nrows);    // dQ
           }
           if (tracer) bw_trace(p, 1 + g, tr, 14, c.n);
         }
@@ -500,7 +493,7 @@ int attention_bwd_tc(const missm_attn_args* a, cudaStream_t stream) {
   p.nc = (p.sw + BW_CW - 1) / BW_CW;
   p.lse = a->lse, p.delta = a->delta;
   p.dqkv = static_cast<__nv_bfloat16*>(a->dqkv), p.ld_qkv = a->ld_qkv, p.q_scale = a->q_scale;
-  const int smem = 4 * BW_RES_BYTES + 4 * BW_TILE_BYTES + 4 * BW_STAT * 4 + static_cast<int>(sizeof(AttnBwdSmem)) + 1024;
+  const int smem = 4 * BW_RES_BYTES + 4 * BW_TILE_BYTES + 4 * BW_STAT * 4 + 8 * 2048 + static_cast<int>(sizeof(AttnBwdSmem)) + 1024;
   static bool configured = false;
   if (!configured) {
     MISSM_CHECK_CUDA(cudaFuncSetAttribute(attn_bwd_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));

@@ -102,6 +102,32 @@ __device__ __forceinline__ float quick_gelu_grad(float x) {
   return fmaf(1.702f * x * s, 1.0f - s, s);
 }
 
+// Warp-collective coalesced store of a 32 x 32 bf16 tile whose rows live one per thread (the layout
+// tcgen05.ld hands out): rows go through a private 2 KB shared staging tile (64-byte pitch, 16-byte
+// chunks XOR-swizzled -> conflict-free both ways) and leave as 16-byte stores covering 8 rows x 64
+// contiguous bytes per instruction, instead of 32 different 128-byte lines per instruction.
+//   v: this thread's row (lane = row), g: global address of element (row 0, col 0), ld in elements,
+//   rows >= nrows are not written.
+__device__ __forceinline__ uint32_t stage64_off(int r, int c) { return r * 64 + ((c ^ ((r >> 1) & 3)) << 4); }
+__device__ __forceinline__ void warp_store_tile32_bf16(uint32_t stage, int lane, const float (&v)[32],
+                                                       __nv_bfloat16* g, long ld, int nrows) {
+#pragma unroll
+  for (int c = 0; c < 4; ++c) {
+    uint4 q;
+    q.x = pack_bf16x2(v[8 * c], v[8 * c + 1]), q.y = pack_bf16x2(v[8 * c + 2], v[8 * c + 3]);
+    q.z = pack_bf16x2(v[8 * c + 4], v[8 * c + 5]), q.w = pack_bf16x2(v[8 * c + 6], v[8 * c + 7]);
+    sts128(stage + stage64_off(lane, c), q);
+  }
+  __syncwarp();
+  const int c = lane & 3;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int r = i * 8 + (lane >> 2);
+    if (r < nrows) *reinterpret_cast<uint4*>(g + r * ld + c * 8) = lds128(stage + stage64_off(r, c));
+  }
+  __syncwarp();
+}
+
 // ----------------------------------------------------------------------------------------
 // mbarrier
 // ----------------------------------------------------------------------------------------
