@@ -65,7 +65,7 @@ typedef struct missm_gemm_args {
   int32_t scale_cols; /* LINEAR: columns [0,scale_cols) are multiplied by col_scale */
   float col_scale;
   int32_t patch_P;    /* PATCH: patches per sample */
-  int32_t split_k;    /* 0 = auto (only LINEAR + out_f32 + no bias may split), 1 = never */
+  int32_t split_k;    /* 0 = auto (only LINEAR + out_f32 + no bias may split), 1 = never, n > 1 = n ways, -1 = stream-K */
   int32_t force_bn;   /* 0 = auto, 128 or 256 = force tile N */
   float* colsum_out;  /* optional [N], PRE-ZEROED: += column sums over m of the fp32 value that is written
                          to C (bias gradient of the consumer layer, fused into the producing GEMM) */

@@ -357,7 +357,7 @@ int attention_fwd_tc(const missm_attn_args* a, cudaStream_t stream) {
     MISSM_CHECK_CUDA(cudaFuncSetAttribute(attn_fwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     configured = true;
   }
-  const int grid = p.n_items < kNumSMs ? p.n_items : kNumSMs;
+  const int grid = p.n_items < persistent_sms() ? p.n_items : persistent_sms();
   const char* trace_path = getenv("MISSM_ATTN_TRACE_FWD");   // debugging aid (synchronises!)
   if (trace_path != nullptr) {
     const size_t nb = 3 * 330 * 3 * sizeof(long long);

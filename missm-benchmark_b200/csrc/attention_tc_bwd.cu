@@ -500,7 +500,7 @@ int attention_bwd_tc(const missm_attn_args* a, cudaStream_t stream) {
     MISSM_CHECK_CUDA(cudaFuncSetAttribute(attn_bwd_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     configured = true;
   }
-  const int grid = p.n_items < kNumSMs ? p.n_items : kNumSMs;
+  const int grid = p.n_items < persistent_sms() ? p.n_items : persistent_sms();
   p.trace = nullptr;
   const char* trace_path = getenv("MISSM_ATTN_TRACE");   // debugging aid: dumps CTA 0's event clocks (synchronises!)
   if (trace_path != nullptr) {

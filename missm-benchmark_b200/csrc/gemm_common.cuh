@@ -28,6 +28,45 @@ struct GemmParams {
   int patch_P;
   int atomic_out;
   float* colsum_out;
+  int stream_k;          // 1: every CTA (pair) owns one contiguous slice of the linearised (tile, k-block) space
+  long sk_per_cta;       //    k-blocks per slice
+};
+
+// The work list of one persistent CTA (pair).  Two schedules:
+//   strided  : unit w = index + i * stride over tiles x uniform K splits (tile = w % tiles, split = w / tiles)
+//   stream-K : one contiguous slice [index * sk_per_cta, ...) of the (tile-major, k-block-minor) sequence;
+//              tiles cut by a slice boundary are accumulated with fp32 atomics into a zeroed C.  Used for
+//              wgrad, whose output grid (48-64 pair tiles, K = 14 906) would leave 14-35 % of the SMs idle.
+struct GemmWork {
+  int tiles_mn, num_kblk, kblk_per_split, total_work, stride, w;
+  long pos, end;
+  bool sk;
+  __device__ __forceinline__ GemmWork(const GemmParams& p, int index, int count) {
+    tiles_mn = p.num_m_blk * p.num_n_blk, num_kblk = p.num_kblk, kblk_per_split = p.kblk_per_split;
+    total_work = tiles_mn * p.num_splits, stride = count, w = index;
+    sk = p.stream_k != 0;
+    const long total = static_cast<long>(tiles_mn) * num_kblk;
+    pos = index * p.sk_per_cta;
+    end = pos + p.sk_per_cta < total ? pos + p.sk_per_cta : total;
+  }
+  // next unit: tile (n fastest: m_blk = tile / num_n_blk) and its k-block range [kb0, kb1)
+  __device__ __forceinline__ bool next(int& tile, int& kb0, int& kb1) {
+    if (sk) {
+      if (pos >= end) return false;
+      tile = static_cast<int>(pos / num_kblk);
+      kb0 = static_cast<int>(pos % num_kblk);
+      const long left = end - pos;
+      kb1 = kb0 + left < num_kblk ? kb0 + static_cast<int>(left) : num_kblk;
+      pos += kb1 - kb0;
+      return true;
+    }
+    if (w >= total_work) return false;
+    tile = w % tiles_mn;
+    kb0 = (w / tiles_mn) * kblk_per_split;
+    kb1 = kb0 + kblk_per_split < num_kblk ? kb0 + kblk_per_split : num_kblk;
+    w += stride;
+    return true;
+  }
 };
 
 template <int BN>

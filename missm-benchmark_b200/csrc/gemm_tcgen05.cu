@@ -213,6 +213,16 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA,
 // ---------------------------------------------------------------------------------------
 static thread_local char g_last_error[512] = "";
 
+int persistent_sms() {
+  static const int v = [] {
+    const char* e = getenv("MISSM_PERSISTENT_SMS");
+    int n = e ? atoi(e) : kNumSMs;
+    if (n < 2 || n > kNumSMs) n = kNumSMs;
+    return n & ~1;
+  }();
+  return v;
+}
+
 void set_last_error(const char* fmt, ...) {
   va_list ap;
   va_start(ap, fmt);
@@ -347,6 +357,7 @@ extern "C" int missm_gemm_bf16(const missm_gemm_args* a, void* stream_v) {
   p.aux_out = a->aux_out, p.ld_aux_out = a->ld_aux_out;
   p.patch_P = a->patch_P;
   p.colsum_out = a->colsum_out;
+  p.stream_k = 0, p.sk_per_cta = 0;
   // large-M problems go to the CTA-pair kernel (gemm_tcgen05_2cta.cu); MISSM_GEMM_1CTA=1 keeps
   // everything on the single-CTA kernel (A/B measurements)
   static const bool only_1cta = getenv("MISSM_GEMM_1CTA") != nullptr;
@@ -354,11 +365,12 @@ extern "C" int missm_gemm_bf16(const missm_gemm_args* a, void* stream_v) {
   p.num_m_blk = (a->M + BM - 1) / BM;
   p.num_kblk = (a->K + BK - 1) / BK;
 
-  // tile-N: pick the shape that wastes fewer SM-waves (148 persistent CTAs)
+  const int nsm = persistent_sms();
+  // tile-N: pick the shape that wastes fewer SM-waves (persistent CTAs)
   auto waves_eff = [&](int bn) {
     long tiles = static_cast<long>(p.num_m_blk) * ((a->N + bn - 1) / bn);
-    long waves = (tiles + kNumSMs - 1) / kNumSMs;
-    return static_cast<double>(tiles) * bn / (static_cast<double>(waves) * kNumSMs * 256.0);
+    long waves = (tiles + nsm - 1) / nsm;
+    return static_cast<double>(tiles) * bn / (static_cast<double>(waves) * nsm * 256.0);
   };
   int bn = 256;
   if (a->force_bn == 128 || a->force_bn == 256)
@@ -375,8 +387,8 @@ extern "C" int missm_gemm_bf16(const missm_gemm_args* a, void* stream_v) {
   if (may_split) {
     if (a->split_k > 1) {
       splits = a->split_k;
-    } else if (tiles * 2 <= kNumSMs && p.num_kblk >= 16) {
-      splits = static_cast<int>((2L * kNumSMs + tiles - 1) / tiles);
+    } else if (tiles * 2 <= nsm && p.num_kblk >= 16) {
+      splits = static_cast<int>((2L * nsm + tiles - 1) / tiles);
       if (splits > p.num_kblk / 8) splits = p.num_kblk / 8;
     }
     if (splits > p.num_kblk) splits = p.num_kblk;
@@ -404,7 +416,7 @@ extern "C" int missm_gemm_bf16(const missm_gemm_args* a, void* stream_v) {
   if (rc) return rc;
 
   const long work = tiles * p.num_splits;
-  const int grid = static_cast<int>(work < kNumSMs ? work : kNumSMs);
+  const int grid = static_cast<int>(work < nsm ? work : nsm);
   if (bn == 256) return dispatch_epi<256>(epi, a->out_f32 != 0, tmA, tmB, p, grid, stream);
   return dispatch_epi<128>(epi, a->out_f32 != 0, tmA, tmB, p, grid, stream);
 }

@@ -80,20 +80,18 @@ gemm_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  const int tiles_mn = p.num_m_blk * p.num_n_blk;   // num_m_blk counts 256-row pair tiles here
-  const int total_work = tiles_mn * p.num_splits;
+  // (p.num_m_blk counts 256-row pair tiles here)
 
   if (warp == 0) {
     // ================================ TMA producer (both CTAs) ========================
     int stage = 0;
     uint32_t phase = 0;
-    for (int w = pair; w < total_work; w += num_pairs) {
-      const int split = w / tiles_mn, rem = w % tiles_mn;
-      const int m_blk = rem / p.num_n_blk, n_blk = rem % p.num_n_blk;
+    GemmWork work(p, pair, num_pairs);
+    int tile, kb0, kb1;
+    while (work.next(tile, kb0, kb1)) {
+      const int m_blk = tile / p.num_n_blk, n_blk = tile % p.num_n_blk;
       const int m0 = m_blk * 256 + static_cast<int>(rank) * 128;
       const int n0 = n_blk * BN + static_cast<int>(rank) * (BN / 2);
-      const int kb0 = split * p.kblk_per_split;
-      const int kb1 = min(kb0 + p.kblk_per_split, p.num_kblk);
       for (int kb = kb0; kb < kb1; ++kb) {
         mbar_wait(&empty_bar[stage], phase ^ 1);
         if (elect_one_sync()) {
@@ -130,10 +128,9 @@ gemm_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
       uint32_t phase = 0;
       int acc = 0;
       uint32_t acc_phase = 0;
-      for (int w = pair; w < total_work; w += num_pairs) {
-        const int split = w / tiles_mn;
-        const int kb0 = split * p.kblk_per_split;
-        const int kb1 = min(kb0 + p.kblk_per_split, p.num_kblk);
+      GemmWork work(p, pair, num_pairs);
+      int tile, kb0, kb1;
+      while (work.next(tile, kb0, kb1)) {
         mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + acc * BN;
@@ -163,9 +160,10 @@ gemm_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
     const uint32_t tempty_leader0 = mapa_shared(smem_u32(&tempty_bar[0]), 0);
     int acc = 0;
     uint32_t acc_phase = 0;
-    for (int w = pair; w < total_work; w += num_pairs) {
-      const int rem = w % tiles_mn;
-      const int m_blk = rem / p.num_n_blk, n_blk = rem % p.num_n_blk;
+    GemmWork work(p, pair, num_pairs);
+    int tile, kb0, kb1;
+    while (work.next(tile, kb0, kb1)) {
+      const int m_blk = tile / p.num_n_blk, n_blk = tile % p.num_n_blk;
       const int row0 = m_blk * 256 + static_cast<int>(rank) * 128 + q * 32;
       // in-place RESID (aux_in aliases C): this warp's tile is only ever touched by this warp, and its
       // loads are issued before its stores
@@ -243,7 +241,7 @@ static int dispatch_epi2(int epi, bool out_f32, const CUtensorMap& a, const CUte
 // Called by missm_gemm_bf16 (gemm_tcgen05.cu) after argument validation; `p` carries everything but
 // the tiling.  Returns -1 if this path declines the shape.
 int gemm_launch_2cta(const missm_gemm_args* a, GemmParams p, cudaStream_t stream) {
-  constexpr int kPairs = kNumSMs / 2;
+  const int kPairs = persistent_sms() / 2;
   p.num_m_blk = (a->M + 255) / 256;
   p.num_kblk = (a->K + BK - 1) / BK;
   auto waves_eff = [&](int bn) {
@@ -265,9 +263,15 @@ int gemm_launch_2cta(const missm_gemm_args* a, GemmParams p, cudaStream_t stream
   if (may_split) {
     if (a->split_k > 1) {
       splits = a->split_k;
-    } else if (tiles * 2 <= kPairs && p.num_kblk >= 16) {
-      splits = static_cast<int>((2L * kPairs + tiles - 1) / tiles);
-      if (splits > p.num_kblk / 8) splits = p.num_kblk / 8;
+    } else if (a->split_k == 0) {
+      // uniform K split s that minimises waves(s) / s, waves(s) = ceil(tiles * s / pairs); only worth the
+      // fp32 atomics (measured) when it removes >= 15 % of the time: 48 tiles (qkv wgrad) -> 3, 16 tiles
+      // (out-proj wgrad) -> 4, 64 tiles (fc wgrad) -> 1
+      double best = 1.0 * ((tiles + kPairs - 1) / kPairs);
+      for (int s = 2; s <= 8 && p.num_kblk / s >= 16; ++s) {
+        const double c = static_cast<double>((tiles * s + kPairs - 1) / kPairs) / s;
+        if (c < 0.85 * best) best = c, splits = s;
+      }
     }
     if (splits > p.num_kblk) splits = p.num_kblk;
     if (splits < 1) splits = 1;
@@ -275,6 +279,18 @@ int gemm_launch_2cta(const missm_gemm_args* a, GemmParams p, cudaStream_t stream
   p.kblk_per_split = (p.num_kblk + splits - 1) / splits;
   p.num_splits = (p.num_kblk + p.kblk_per_split - 1) / p.kblk_per_split;
   p.atomic_out = p.num_splits > 1 ? 1 : 0;
+  // stream-K (split_k = -1): kept for experiments -- on the wgrad shapes the extra atomic epilogues cost
+  // more than the idle SMs they fill (fc wgrad 92 -> 106-115 us)
+  p.stream_k = 0, p.sk_per_cta = 0;
+  long work = tiles * p.num_splits;
+  int grid_pairs = static_cast<int>(work < kPairs ? work : kPairs);
+  if (may_split && a->split_k == -1 && p.num_kblk >= 32) {
+    const long total = tiles * p.num_kblk;
+    p.stream_k = 1, p.atomic_out = 1;
+    p.sk_per_cta = (total + kPairs - 1) / kPairs;
+    if (p.sk_per_cta < 8) p.sk_per_cta = 8;
+    grid_pairs = static_cast<int>((total + p.sk_per_cta - 1) / p.sk_per_cta);
+  }
   if (p.atomic_out) {
     MISSM_CHECK_CUDA(cudaMemset2DAsync(a->C, static_cast<size_t>(a->ldc) * 4, 0, static_cast<size_t>(a->N) * 4, a->M,
                                        stream));
@@ -293,8 +309,7 @@ int gemm_launch_2cta(const missm_gemm_args* a, GemmParams p, cudaStream_t stream
     rc = make_tmap_2d_bf16(&tmB, a->B, a->N, a->K, a->ldb, 64, BK);
   if (rc) return rc;
 
-  const long work = tiles * p.num_splits;
-  const int grid = 2 * static_cast<int>(work < kPairs ? work : kPairs);
+  const int grid = 2 * grid_pairs;
   if (bn == 256) return dispatch_epi2<256>(a->epilogue, a->out_f32 != 0, tmA, tmB, p, grid, stream);
   return dispatch_epi2<128>(a->epilogue, a->out_f32 != 0, tmA, tmB, p, grid, stream);
 }

@@ -10,6 +10,10 @@
 namespace missm {
 
 constexpr int kNumSMs = 148;  // B200: 2 dies x 74 SMs
+// SMs the persistent kernels (GEMM, tcgen05 attention) spread over.  Default: all 148.  Under data
+// parallelism MISSM_PERSISTENT_SMS (even, e.g. 132) leaves a few SMs to NCCL's all-reduce CTAs, which
+// cannot co-reside with one-CTA-per-SM kernels that own the whole register file and shared memory.
+int persistent_sms();
 
 // ----------------------------------------------------------------------------------------
 // error plumbing (host)
