@@ -98,10 +98,12 @@ typedef struct missm_attn_args {
   int32_t n_seq, s_in;
   int32_t causal, mask_div;
   float q_scale; /* bwd: dq is multiplied by this */
+  float* dqkv_colsum;     /* bwd, optional [3D], PRE-ZEROED: += column sums of dqkv (the q/k/v bias gradients) */
+  int32_t colsum_done;    /* bwd, OUT: 1 if the kernels filled dqkv_colsum, 0 if the caller has to reduce dqkv */
 } missm_attn_args;
 
 int missm_attention_fwd(const missm_attn_args* args, void* stream);
-int missm_attention_bwd(const missm_attn_args* args, void* stream);
+int missm_attention_bwd(missm_attn_args* args, void* stream);   /* writes args->colsum_done */
 
 /* ---------------------------------------------------------------------------------------
  * LayerNorm over rows of the fp32 residual stream (nn.LayerNorm at modeling_image.py:120,132,

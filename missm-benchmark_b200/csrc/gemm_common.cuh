@@ -196,22 +196,6 @@ __device__ __forceinline__ void tile_stg(void* base, long ld, int col0, int ncol
   }
 }
 
-// sum over the 32 lanes of v[c] for every column c: butterfly "transpose-reduce" (31 shuffles);
-// returns in lane l the total of column l.  Destroys v.
-__device__ __forceinline__ float warp_colsum32(float (&v)[32], int lane) {
-#pragma unroll
-  for (int s = 16; s >= 1; s >>= 1) {
-    const bool up = (lane & s) != 0;
-#pragma unroll
-    for (int i = 0; i < s; ++i) {
-      const float send = up ? v[i] : v[i + s];
-      const float keep = up ? v[i + s] : v[i];
-      v[i] = keep + __shfl_xor_sync(0xffffffffu, send, s);
-    }
-  }
-  return v[0];
-}
-
 // `row0`: global row of this warp's lane 0; `acc`: this thread's row (row0 + lane) of the fp32
 // accumulator, columns [col0, col0 + 32).  All 32 lanes must call (warp-collective).
 // The auxiliary input tile of a chunk (residual / pre-activation / position rows), as coalesced

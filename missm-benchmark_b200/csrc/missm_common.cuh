@@ -106,6 +106,22 @@ __device__ __forceinline__ float quick_gelu_grad(float x) {
   return fmaf(1.702f * x * s, 1.0f - s, s);
 }
 
+// sum over the 32 lanes of v[c] for every column c: butterfly "transpose-reduce" (31 shuffles);
+// returns in lane l the total of column l.  Destroys v.
+__device__ __forceinline__ float warp_colsum32(float (&v)[32], int lane) {
+#pragma unroll
+  for (int s = 16; s >= 1; s >>= 1) {
+    const bool up = (lane & s) != 0;
+#pragma unroll
+    for (int i = 0; i < s; ++i) {
+      const float send = up ? v[i] : v[i + s];
+      const float keep = up ? v[i + s] : v[i];
+      v[i] = keep + __shfl_xor_sync(0xffffffffu, send, s);
+    }
+  }
+  return v[0];
+}
+
 // Warp-collective coalesced store of a 32 x 32 bf16 tile whose rows live one per thread (the layout
 // tcgen05.ld hands out): rows go through a private 2 KB shared staging tile (64-byte pitch, 16-byte
 // chunks XOR-swizzled -> conflict-free both ways) and leave as 16-byte stores covering 8 rows x 64

@@ -28,6 +28,7 @@ class AttnArgs(ctypes.Structure):
         ("n_seq", ctypes.c_int32), ("s_in", ctypes.c_int32),
         ("causal", ctypes.c_int32), ("mask_div", ctypes.c_int32),
         ("q_scale", ctypes.c_float),
+        ("dqkv_colsum", ctypes.c_void_p), ("colsum_done", ctypes.c_int32),
     ]
 
 

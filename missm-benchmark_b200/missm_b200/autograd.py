@@ -130,10 +130,9 @@ class AttnBlockFn(torch.autograd.Function):
         d_out_b, d_ob = _bf16_of(d_out)
         d_ow = ops.gemm(d_out_b, attn, a_mn=True, b_mn=True, out_dtype=F32)          # dY^T @ attn
         d_attn = ops.gemm(d_out_b, wo, b_mn=True)                                      # dY @ Wo
-        dqkv = ops.attention_bwd(qkv, attn, lse, d_attn, meta.layout, meta.H, hd ** -0.5, causal=meta.causal,
-                                 key_mask=meta.key_mask, mask_rows=meta.mask_rows, mask_div=meta.mask_div)
+        dqkv, d_bqkv = ops.attention_bwd(qkv, attn, lse, d_attn, meta.layout, meta.H, hd ** -0.5, causal=meta.causal,
+                                         key_mask=meta.key_mask, mask_rows=meta.mask_rows, mask_div=meta.mask_div)
         d_wqkv = ops.gemm(dqkv, h, a_mn=True, b_mn=True, out_dtype=F32)               # [3D, D]
-        d_bqkv = ops.colsum(dqkv)
         d_h = ops.gemm(dqkv, wqkv, b_mn=True)
         dx, dx_b, d_lnw, d_lnb, dx_cs = ops.layernorm_bwd(d_h, x_res, mean, rstd, ln_w, dres=d_out, want_bf16=True)
         _publish_bf16(dx, dx_b, dx_cs)

@@ -22,10 +22,10 @@ def run(S,H,N,bench=False):
     ref_o=ref.permute(0,2,1,3).reshape(S*N,D)
     d_out=torch.randn(S*N,D,device=dev).bfloat16()
     ref_o.backward(d_out.float())
-    dqkv=ops.attention_bwd(qkv,out,lse,d_out,lay,H,0.125)
+    dqkv,dcs=ops.attention_bwd(qkv,out,lse,d_out,lay,H,0.125)
     torch.cuda.synchronize()
     g=f.grad.permute(1,3,0,2,4).reshape(S*N,3*D).clone(); g[:,:D]*=0.125
-    print(f"S={S} H={H} N={N}: fwd {rel(out,ref_o):.2e} dq {rel(dqkv[:,:D],g[:,:D]):.2e} dk {rel(dqkv[:,D:2*D],g[:,D:2*D]):.2e} dv {rel(dqkv[:,2*D:],g[:,2*D:]):.2e}", flush=True)
+    print(f"S={S} H={H} N={N}: fwd {rel(out,ref_o):.2e} dq {rel(dqkv[:,:D],g[:,:D]):.2e} dk {rel(dqkv[:,D:2*D],g[:,D:2*D]):.2e} dv {rel(dqkv[:,2*D:],g[:,2*D:]):.2e} cs {rel(dcs,g.sum(0)):.2e}", flush=True)
     if bench:
         fl=4*N*N*64*S*H
         ms=t(lambda: ops.attention_fwd(qkv,lay,H)); print(f"  fwd {ms*1e3:.1f} us {fl/ms/1e9:.0f} TF/s")

@@ -9,6 +9,6 @@ lay=ops.SeqLayout.spatial(S,N)
 d_out=torch.randn(S*N,D,device="cuda").bfloat16()
 for _ in range(2):
     out,lse=ops.attention_fwd(qkv,lay,H)
-    dqkv=ops.attention_bwd(qkv,out,lse,d_out,lay,H,0.125)
+    dqkv,dcs=ops.attention_bwd(qkv,out,lse,d_out,lay,H,0.125)
 torch.cuda.synchronize()
 print("ok")

@@ -176,12 +176,13 @@ def test_attention_fwd_bwd(ops, cfg):
     d_out = (torch.randn(S * N, D, device=DEV)).bfloat16()
     ref_o.backward(d_out.float())
     q_scale = 0.125
-    dqkv = ops.attention_bwd(qkv, out, lse, d_out, lay, H, q_scale, causal=causal, key_mask=kmask)
+    dqkv, dcs = ops.attention_bwd(qkv, out, lse, d_out, lay, H, q_scale, causal=causal, key_mask=kmask)
     gref = f.grad.permute(1, 3, 0, 2, 4).reshape(S * N, 3 * D).clone()
     gref[:, :D] *= q_scale
     assert rel(dqkv[:, :D], gref[:, :D]) < 1.5e-2
     assert rel(dqkv[:, D:2 * D], gref[:, D:2 * D]) < 1.5e-2
     assert rel(dqkv[:, 2 * D:], gref[:, 2 * D:]) < 1.5e-2
+    assert rel(dcs, gref.sum(0)) < 1.5e-2               # q/k/v bias gradients
 
 
 def test_attention_temporal_layout(ops):
