@@ -553,7 +553,6 @@ extern "C" int missm_attention_bwd(missm_attn_args* a, void* stream) {
   static const bool legacy_only = getenv("MISSM_ATTN_LEGACY") != nullptr;
   if (!legacy_only) {
     const int rc = attention_bwd_tc(a, st);   // tcgen05 path for the shapes it covers
-    if (rc == 0 && a->dqkv_colsum != nullptr) a->colsum_done = 1;
     if (rc >= 0) return rc;
   }
   dim3 grid((p.N + TILE - 1) / TILE, p.H, p.n_seq);

@@ -42,6 +42,7 @@ struct AttnFwdTcParams {
   long long* trace;       // debugging only (MISSM_ATTN_TRACE_FWD): (tag, tile, clock) events of CTA 0
 };
 
+#ifdef MISSM_ATTN_TRACE_BUILD   // timeline tracing is compiled out of the production kernels (registers)
 __device__ __forceinline__ void fw_trace(const AttnFwdTcParams& p, int slot, uint32_t& cnt, int tag, uint32_t n) {
   if (p.trace != nullptr && blockIdx.x == 0 && cnt < 330) {
     long long* t = p.trace + (slot * 330 + cnt) * 3;
@@ -49,6 +50,9 @@ __device__ __forceinline__ void fw_trace(const AttnFwdTcParams& p, int slot, uin
     ++cnt;
   }
 }
+#else
+__device__ __forceinline__ void fw_trace(const AttnFwdTcParams&, int, uint32_t&, int, uint32_t) {}
+#endif
 
 struct AttnFwdSmem {
   uint64_t kv_full[2], kv_empty[2];

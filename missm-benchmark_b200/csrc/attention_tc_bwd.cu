@@ -48,10 +48,10 @@ struct AttnBwdTcParams {
   __nv_bfloat16* dqkv;
   long ld_qkv;
   float q_scale;
-  float* dqkv_colsum;  // [3D] pre-zeroed, or null
   long long* trace;    // debugging only (MISSM_ATTN_TRACE): [4096] x (tag, step, clock) of CTA 0
 };
 
+#ifdef MISSM_ATTN_TRACE_BUILD   // timeline tracing is compiled out of the production kernels (registers)
 __device__ __forceinline__ void bw_trace(const AttnBwdTcParams& p, int slot_base, uint32_t& cnt, int tag, uint32_t n) {
   if (p.trace != nullptr && blockIdx.x == 0 && cnt < 330) {
     long long* t = p.trace + (slot_base * 330 + cnt) * 3;
@@ -59,6 +59,9 @@ __device__ __forceinline__ void bw_trace(const AttnBwdTcParams& p, int slot_base
     ++cnt;
   }
 }
+#else
+__device__ __forceinline__ void bw_trace(const AttnBwdTcParams&, int, uint32_t&, int, uint32_t) {}
+#endif
 
 struct AttnBwdSmem {
   uint64_t res_full[2], res_empty[2];
@@ -147,19 +150,15 @@ __device__ __forceinline__ void bwd_chunk(uint32_t t_s, uint32_t t_dp, uint32_t 
 }
 
 // accumulator rows (one per thread, 64 fp32 columns in two 32-column register blocks) -> bf16 -> HBM
-// and, if csum != null, their column sums (over the valid rows) += csum[0..63]  (bias gradient)
 __device__ __forceinline__ void store_rows64_bf16(uint32_t stage, int lane, const uint32_t (&a)[32], const uint32_t (&b)[32],
-                                                  float scale, __nv_bfloat16* g, long ld, int nrows, float* csum) {
+                                                  float scale, __nv_bfloat16* g, long ld, int nrows) {
   float v[32];
-  const float keep = lane < nrows ? scale : 0.f;      // rows past the sequence end hold garbage accumulators
 #pragma unroll
-  for (int j = 0; j < 32; ++j) v[j] = lane < nrows ? __uint_as_float(a[j]) * keep : 0.f;
+  for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(a[j]) * scale;
   warp_store_tile32_bf16(stage, lane, v, g, ld, nrows);
-  if (csum != nullptr) atomicAdd(csum + lane, warp_colsum32(v, lane));
 #pragma unroll
-  for (int j = 0; j < 32; ++j) v[j] = lane < nrows ? __uint_as_float(b[j]) * keep : 0.f;
+  for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(b[j]) * scale;
   warp_store_tile32_bf16(stage, lane, v, g + 32, ld, nrows);
-  if (csum != nullptr) atomicAdd(csum + 32 + lane, warp_colsum32(v, lane));
 }
 
 // tm128 / tm16: [3D cols, N rows, n_seq] views of qkv with 64 x 128 and 64 x 16 boxes; td128 / td16:
@@ -436,21 +435,20 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm128, const __grid_const
           const int wrow0 = c.tile * 128 + q * 32;            // first row of this warp
           __nv_bfloat16* grow = p.dqkv + (static_cast<long>(s) * p.N + wrow0) * p.ld_qkv + h * 64;
           const int nrows = p.N - wrow0;
-          float* cs = p.dqkv_colsum ? p.dqkv_colsum + h * 64 : nullptr;
           if constexpr (DKV) {
             uint32_t x0[32], x1[32];
             if (warp_has_rows) {
               tmem_ld_32x32b_x32(tmem + lane_addr + BW_ACC_COL, x0);
               tmem_ld_32x32b_x32(tmem + lane_addr + BW_ACC_COL + 32, x1);
               tmem_ld_wait();
-              store_rows64_bf16(stage, lane, x0, x1, 1.0f, grow + 2 * p.D, p.ld_qkv, nrows, cs ? cs + 2 * p.D : nullptr);     // dV
+              store_rows64_bf16(stage, lane, x0, x1, 1.0f, grow + 2 * p.D, p.ld_qkv, nrows);     // dV
               tmem_ld_32x32b_x32(tmem + lane_addr + BW_ACC_COL + 64, x0);
               tmem_ld_32x32b_x32(tmem + lane_addr + BW_ACC_COL + 96, x1);
               tmem_ld_wait();
             }
             tc_fence_before();
             mbar_arrive(&sh->acc_empty[acc]);
-            if (warp_has_rows) store_rows64_bf16(stage, lane, x0, x1, 1.0f, grow + p.D, p.ld_qkv, nrows, cs ? cs + p.D : nullptr);   // dK
+            if (warp_has_rows) store_rows64_bf16(stage, lane, x0, x1, 1.0f, grow + p.D, p.ld_qkv, nrows);   // dK
           } else {
             uint32_t x0[32], x1[32];
             if (warp_has_rows) {
@@ -460,7 +458,7 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm128, const __grid_const
             }
             tc_fence_before();
             mbar_arrive(&sh->acc_empty[acc]);
-            if (warp_has_rows) store_rows64_bf16(stage, lane, x0, x1, p.q_scale, grow, p.ld_qkv, nrows, cs);    // dQ
+            if (warp_has_rows) store_rows64_bf16(stage, lane, x0, x1, p.q_scale, grow, p.ld_qkv, nrows);    // dQ
           }
           if (tracer) bw_trace(p, 1 + g, tr, 14, c.n);
         }
@@ -499,7 +497,6 @@ int attention_bwd_tc(const missm_attn_args* a, cudaStream_t stream) {
   p.nc = (p.sw + BW_CW - 1) / BW_CW;
   p.lse = a->lse, p.delta = a->delta;
   p.dqkv = static_cast<__nv_bfloat16*>(a->dqkv), p.ld_qkv = a->ld_qkv, p.q_scale = a->q_scale;
-  p.dqkv_colsum = a->dqkv_colsum;
   const int smem = 4 * BW_RES_BYTES + 4 * BW_TILE_BYTES + 4 * BW_STAT * 4 + 8 * 2048 + static_cast<int>(sizeof(AttnBwdSmem)) + 1024;
   static bool configured = false;
   if (!configured) {

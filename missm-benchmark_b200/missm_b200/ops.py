@@ -18,7 +18,6 @@ BF16, F32 = torch.bfloat16, torch.float32
 # around every GEMM launch on the launching stream: list of (start, end, flop)
 LAUNCHES = [0]
 GEMM_TIMING = None
-_FUSE_ATTN_COLSUM = os.environ.get("MISSM_AB_ATTN_COLSUM") is not None
 
 
 def _p(t):
@@ -129,19 +128,14 @@ def attention_fwd(qkv, lay, H, *, causal=False, key_mask=None, mask_rows=None, m
 def attention_bwd(qkv, out, lse, d_out, lay, H, q_scale, *, causal=False, key_mask=None,
                   mask_rows=None, mask_div=1):
     """-> (dqkv bf16 [rows, 3D], column sums of dqkv f32 [3D] = the q/k/v bias gradients); the q block is
-    the gradient w.r.t. the UN-scaled projection.  The tcgen05 kernels CAN emit the column sums from
-    their epilogues (MISSM_AB_ATTN_COLSUM=1); by default one extra HBM-bound pass over dqkv does."""
+    the gradient w.r.t. the UN-scaled projection.  (Emitting the column sums from the kernels' epilogues
+    was measured slower -- contended atomics -- so one extra HBM-bound pass over dqkv computes them.)"""
     assert d_out.dtype == BF16 and d_out.shape == out.shape and _ld(d_out) == _ld(out)
     dqkv = torch.empty_like(qkv)
     delta = torch.empty_like(lse)
     a = _attn_args(qkv, out, lse, lay, H, causal, key_mask, mask_rows, mask_div)
     a.d_out, a.delta, a.dqkv, a.q_scale = d_out.data_ptr(), delta.data_ptr(), dqkv.data_ptr(), q_scale
     csum = None
-    if _FUSE_ATTN_COLSUM:
-        # measured: the per-column atomics from 148 CTAs contend (bwd 222 -> 282 us) and cost more than
-        # the separate 26 us pass; kept behind a switch
-        csum = torch.zeros((qkv.shape[1],), device=qkv.device, dtype=F32)
-        a.dqkv_colsum = csum.data_ptr()
     a.colsum_done = 0
     LAUNCHES[0] += 3
     check(lib().missm_attention_bwd(ctypes.byref(a), stream_ptr()), "attention_bwd")
