@@ -233,12 +233,16 @@ def run_gpu_arm(a):
             dist.barrier()
         torch.cuda.synchronize()
 
+    host_ms = [0.0]
+
     def timed(fn, steps):
         barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
+        h0 = time.perf_counter()
         for _ in range(steps):
             fn()
+        host_ms[0] = (time.perf_counter() - h0) * 1e3 / steps      # time the host needs to ISSUE a step
         e1.record()
         barrier()
         ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
@@ -252,6 +256,7 @@ def run_gpu_arm(a):
     ops.LAUNCHES[0] = 0
     ms = timed(step_resident, a.steps)
     launches = ops.LAUNCHES[0]
+    host_issue_ms = host_ms[0]
     clocks = sampler.stop() if sampler else None
     samples_per_s = world * B * a.steps / (ms / 1e3)
 
@@ -308,6 +313,7 @@ def run_gpu_arm(a):
             "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
             "config": {"workload": WORKLOAD, "batch_per_gpu": B, "missing_ratio": a.missing,
                        "missing_samples": n_missing, "fusion": "sum", "layers": a.layers, "tower_streams": bool(model.encoder.tower_streams),
+                       "host_issue_ms_per_step": host_issue_ms,
                        "step": "zero_grad + forward + CrossEntropy + backward (DDP allreduce at N>1); optimizer excluded (metric is fwd+bwd)",
                        "l2": "working set >> 126 MB L2 every step (1.8 GB bf16 weights + >30 GB activations)",
                        "encoder_tflops_algorithmic": algo_tf,

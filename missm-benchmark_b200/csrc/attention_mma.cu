@@ -549,12 +549,12 @@ extern "C" int missm_attention_bwd(missm_attn_args* a, void* stream) {
   const long total = static_cast<long>(p.n_seq) * p.H * p.N;
   int dgrid = static_cast<int>((total + 255) / 256);
   if (dgrid > 16 * kNumSMs) dgrid = 16 * kNumSMs;
-  attn_delta_kernel<<<dgrid, 256, 0, st>>>(p);
   static const bool legacy_only = getenv("MISSM_ATTN_LEGACY") != nullptr;
   if (!legacy_only) {
-    const int rc = attention_bwd_tc(a, st);   // tcgen05 path for the shapes it covers
+    const int rc = attention_bwd_tc(a, st);   // tcgen05 path for the shapes it covers (computes delta itself)
     if (rc >= 0) return rc;
   }
+  attn_delta_kernel<<<dgrid, 256, 0, st>>>(p);
   dim3 grid((p.N + TILE - 1) / TILE, p.H, p.n_seq);
   attn_bwd_dkv_kernel<<<grid, kAttnThreads, 0, st>>>(p);
   attn_bwd_dq_kernel<<<grid, kAttnThreads, 0, st>>>(p);

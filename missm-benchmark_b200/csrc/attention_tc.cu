@@ -21,11 +21,12 @@
 #include <cstdlib>
 
 #include "../../include/missm_b200.h"
+#include "attention_tail.cuh"
 #include "missm_common.cuh"
 
 namespace missm {
 
-constexpr int FW_THREADS = 384;            // warp 0 TMA, 1 MMA, 2 TMEM alloc, 4-11 softmax
+constexpr int FW_THREADS = 384;            // warp 0 TMA, 1 MMA, 2 TMEM alloc, 2-3 odd-row tail, 4-11 softmax
 constexpr int FW_MAXN = 272;
 constexpr int FW_KV_BYTES = FW_MAXN * 128; // one resident operand
 constexpr int FW_TILE_BYTES = 128 * 128;
@@ -36,6 +37,9 @@ struct AttnFwdTcParams {
   int N, H, D, n_items;
   int sw;                 // N rounded up to 16
   int nt;                 // query tiles per item
+  int tail;               // 1: row N-1 is computed by warps 2-3 on the CUDA cores (attention_tail.cuh), tiles cover [0, N-1)
+  const __nv_bfloat16* qkv;
+  long ld_qkv;
   __nv_bfloat16* out;
   long ld_o;
   float* lse;             // [n_seq, H, N] or null
@@ -61,6 +65,9 @@ struct AttnFwdSmem {
   uint32_t tmem_base;
   float xmax[2][128];     // row max / row sum halves exchanged between the two warps of a row
   float xsum[2][128];
+  float tail_w[kTailW];         // odd row: P
+  float tail_x[4];              //          max / sum halves of the two tail warps
+  float tail_part[64];          //          partial output of warp 3
 };
 
 __device__ __forceinline__ void fw_named_sync() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
@@ -80,7 +87,7 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm128, const __grid_const
   if (warp == 0 && lane == 0) tma_prefetch_desc(&tm128), tma_prefetch_desc(&tm16);
   if (warp == 1 && lane == 0) {
     for (int i = 0; i < 2; ++i) {
-      mbar_init(&sh->kv_full[i], 1), mbar_init(&sh->kv_empty[i], 1);
+      mbar_init(&sh->kv_full[i], 1), mbar_init(&sh->kv_empty[i], p.tail ? 3 : 1);   // MMA commit (+ the two tail warps)
       mbar_init(&sh->q_full[i], 1), mbar_init(&sh->q_empty[i], 1);
     }
     mbar_init(&sh->s_full, 1), mbar_init(&sh->o_full, 1);
@@ -188,6 +195,63 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm128, const __grid_const
       }
       __syncwarp();
       if (lane == 0) fw_trace(p, 0, tr, 5, tc);
+    }
+  } else if (warp < 4) {
+    // ========================= the odd row N-1 on the CUDA cores (warps 2 + 3) =========
+    if (p.tail) {
+      const int tw = warp - 2, t = tw * 32 + lane;
+      const uint32_t w_s = smem_u32(sh->tail_w);
+      uint32_t it = 0;
+      for (int item = blockIdx.x; item < p.n_items; item += gridDim.x, ++it) {
+        const int s = item / p.H, h = item % p.H, kb = it & 1;
+        const long row = static_cast<long>(s) * p.N + (p.N - 1);
+        float a[64];
+        tail_load_row64(p.qkv + row * p.ld_qkv + h * 64, a);       // q (pre-scaled)
+        mbar_wait(&sh->kv_full[kb], (it >> 1) & 1);
+        const uint32_t k_s = smem_u32(sKV + (kb * 2 + 0) * FW_KV_BYTES);
+        const uint32_t v_s = smem_u32(sKV + (kb * 2 + 1) * FW_KV_BYTES);
+        float sc[kTailSlots];
+        float mx = -INFINITY;
+#pragma unroll
+        for (int j = 0; j < kTailSlots; ++j) {
+          const int r = t + 64 * j;
+          sc[j] = r < p.N ? tail_dot64(k_s, r, a) : -INFINITY;
+          mx = fmaxf(mx, sc[j]);
+        }
+        mx = warp_max(mx);
+        if (lane == 0) sh->tail_x[tw] = mx;
+        tail_team_sync();
+        mx = fmaxf(sh->tail_x[0], sh->tail_x[1]);
+        float sum = 0.f;
+#pragma unroll
+        for (int j = 0; j < kTailSlots; ++j) {
+          const int r = t + 64 * j;
+          const float e = r < p.N ? fast_ex2((sc[j] - mx) * kLog2eFw) : 0.f;
+          sum += e;
+          sts_f32(w_s + r * 4, e);
+        }
+        sum = warp_sum(sum);
+        if (lane == 0) sh->tail_x[2 + tw] = sum;
+        tail_team_sync();                                // weights and partial sums are visible
+        sum = sh->tail_x[2] + sh->tail_x[3];
+        float acc[8];
+        tail_weighted_rowsum(v_s, w_s, tw == 0 ? 0 : 128, tw == 0 ? 128 : p.N, lane, acc);
+        __syncwarp();                                    // every lane is done with K, V
+        if (lane == 0) mbar_arrive(&sh->kv_empty[kb]);
+        if (tw == 1 && lane < 8) {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) sh->tail_part[lane * 8 + j] = acc[j];
+        }
+        tail_team_sync();
+        if (tw == 0) {
+          if (lane < 8) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) acc[j] += sh->tail_part[lane * 8 + j];
+          }
+          tail_store_row64(p.out + row * p.ld_o + h * 64, lane, acc, 1.0f / sum);
+          if (lane == 0 && p.lse != nullptr) p.lse[static_cast<long>(item) * p.N + p.N - 1] = mx + __logf(sum);
+        }
+      }
     }
   } else if (warp >= 4) {
     // ========================= softmax + output ========================================
@@ -352,7 +416,10 @@ int attention_fwd_tc(const missm_attn_args* a, cudaStream_t stream) {
   AttnFwdTcParams p;
   p.N = a->N, p.H = a->H, p.D = a->D, p.n_items = a->n_seq * a->H;
   p.sw = (a->N + 15) / 16 * 16;
-  p.nt = (a->N + 127) / 128;
+  p.tail = attention_tail_enabled(a->N) ? 1 : 0;
+  p.nt = p.tail ? a->N / 128 : (a->N + 127) / 128;
+  if (p.tail && getenv("MISSM_ATTN_TAIL_SKIP") != nullptr) p.tail = 0;   // TIMING EXPERIMENT ONLY: row N-1 is left uncomputed
+  p.qkv = static_cast<const __nv_bfloat16*>(a->qkv), p.ld_qkv = a->ld_qkv;
   p.out = static_cast<__nv_bfloat16*>(a->out), p.ld_o = a->ld_o, p.lse = a->lse;
   p.trace = nullptr;
   const int smem = 4 * FW_KV_BYTES + 2 * FW_TILE_BYTES + 8 * 2048 + static_cast<int>(sizeof(AttnFwdSmem)) + 1024;

@@ -25,11 +25,12 @@
 #include <cstdlib>
 
 #include "../../include/missm_b200.h"
+#include "attention_tail.cuh"
 #include "missm_common.cuh"
 
 namespace missm {
 
-constexpr int BW_THREADS = 384;      // warp 0 TMA, 1 MMA, 2 TMEM alloc, 3 column statistics, 4-7 / 8-11 softmax WGs
+constexpr int BW_THREADS = 384;      // warp 0 TMA, 1 MMA, 2 TMEM alloc, 3 column statistics, 2-3 odd-row tail, 4-7 / 8-11 softmax WGs
 constexpr int BW_CW = 96;            // score chunk width (columns)
 constexpr int BW_MAXN = 272;         // resident rows (multiple of 16)
 constexpr int BW_RES_BYTES = BW_MAXN * 128;   // one resident operand (rows of 64 bf16)
@@ -43,6 +44,11 @@ struct AttnBwdTcParams {
   int sw;      // N rounded up to 16
   int nt;      // row tiles (128 rows)
   int nc;      // column chunks
+  int tail;    // DQ only, 1: query row N-1 is computed by warps 2-3 on the CUDA cores (tiles cover [0, N-1));
+               // DKV gets nt = (N-1)/128 with tail = 0: its key row N-1 comes from attn_delta_tail_kernel
+  const __nv_bfloat16* qkv;
+  const __nv_bfloat16* d_out;
+  long ld_o;
   const float* lse;    // [n_seq, H, N]
   const float* delta;  // [n_seq, H, N]
   __nv_bfloat16* dqkv;
@@ -70,6 +76,7 @@ struct AttnBwdSmem {
   uint64_t acc_full[2], acc_empty[2];
   uint64_t stat_full[2], stat_empty[2];
   uint32_t tmem_base;
+  float tail_w[2][kTailW];   // odd row: P | dS (DQ: dS | partial dQ of warp 3)
 };
 
 // position in the flattened (item, row tile, column chunk) sequence of this CTA
@@ -185,7 +192,7 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm128, const __grid_const
   }
   if (warp == 1 && lane == 0) {
     for (int i = 0; i < 2; ++i) {
-      mbar_init(&sh->res_full[i], 1), mbar_init(&sh->res_empty[i], 1);
+      mbar_init(&sh->res_full[i], 1), mbar_init(&sh->res_empty[i], p.tail ? 3 : 1);   // MMA commit (+ the two tail warps)
       mbar_init(&sh->a_full[i], 1), mbar_init(&sh->a_empty[i], 1);
       mbar_init(&sh->s_full[i], 1), mbar_init(&sh->p_full[i], 128), mbar_init(&sh->sbuf_empty[i], 1);
       mbar_init(&sh->acc_full[i], 1), mbar_init(&sh->acc_empty[i], 128);
@@ -347,11 +354,10 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm128, const __grid_const
         cp.advance(p);
       }
     }
-  } else if (warp == 3) {
-    // ===================== column statistics (DKV): -lse*log2e and delta per query ===========
+  } else if (warp < 4) {
+    // ===== warp 3: column statistics (DKV): -lse*log2e and delta per query;  warps 2 + 3: the odd row =====
     if constexpr (DKV) {
-      uint32_t it = 0;
-      for (int item = blockIdx.x; item < p.n_items; item += gridDim.x, ++it) {
+      auto load_stats = [&](uint32_t it, int item) {
         const int sbuf = it & 1;
         mbar_wait(&sh->stat_empty[sbuf], ((it >> 1) & 1) ^ 1);
         float* nl = sStat + (sbuf * 2 + 0) * BW_STAT;
@@ -363,6 +369,59 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm128, const __grid_const
           de[q] = ok ? p.delta[base + q] : 0.f;
         }
         mbar_arrive(&sh->stat_full[sbuf]);
+      };
+      // (the odd KEY row of DKV is not computed here: attn_delta_tail_kernel does it, see below)
+      if (warp == 3) {
+        uint32_t it = 0;
+        for (int item = blockIdx.x; item < p.n_items; item += gridDim.x, ++it) load_stats(it, item);
+      }
+    } else {
+      if (p.tail) {
+        // ---- query N-1: dQ[N-1] = q_scale * sum_k dS[k] K[k]
+        const int tw = warp - 2, t = tw * 32 + lane;
+        const uint32_t w0_s = smem_u32(sh->tail_w[0]), w1_s = smem_u32(sh->tail_w[1]);
+        uint32_t it = 0;
+        for (int item = blockIdx.x; item < p.n_items; item += gridDim.x, ++it) {
+          const int s = item / p.H, h = item % p.H, rb = it & 1;
+          const long row = static_cast<long>(s) * p.N + (p.N - 1);
+          const long li = static_cast<long>(item) * p.N + (p.N - 1);
+          const float nl = -p.lse[li] * kLog2eBw, de = p.delta[li];
+          float a[64], sc[kTailSlots];
+          tail_load_row64(p.qkv + row * p.ld_qkv + h * 64, a);             // q (pre-scaled)
+          mbar_wait(&sh->res_full[rb], (it >> 1) & 1);
+          const uint32_t k_s = smem_u32(sRes + (rb * 2 + 0) * BW_RES_BYTES);
+          const uint32_t v_s = smem_u32(sRes + (rb * 2 + 1) * BW_RES_BYTES);
+#pragma unroll
+          for (int j = 0; j < kTailSlots; ++j) {
+            const int r = t + 64 * j;
+            sc[j] = r < p.N ? tail_dot64(k_s, r, a) : 0.f;
+          }
+          tail_load_row64(p.d_out + row * p.ld_o + h * 64, a);             // dO
+#pragma unroll
+          for (int j = 0; j < kTailSlots; ++j) {
+            const int r = t + 64 * j;
+            float ds = 0.f;
+            if (r < p.N) ds = fast_ex2(fmaf(sc[j], kLog2eBw, nl)) * (tail_dot64(v_s, r, a) - de);
+            sts_f32(w0_s + r * 4, ds);
+          }
+          tail_team_sync();
+          float dq[8];
+          tail_weighted_rowsum(k_s, w0_s, tw == 0 ? 0 : 128, tw == 0 ? 128 : p.N, lane, dq);
+          __syncwarp();                                    // every lane is done with K, V
+          if (lane == 0) mbar_arrive(&sh->res_empty[rb]);
+          if (tw == 1 && lane < 8) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) sts_f32(w1_s + (lane * 8 + j) * 4, dq[j]);
+          }
+          tail_team_sync();
+          if (tw == 0) {
+            if (lane < 8) {
+#pragma unroll
+              for (int j = 0; j < 8; ++j) dq[j] += lds_f32(w1_s + (lane * 8 + j) * 4);
+            }
+            tail_store_row64(p.dqkv + row * p.ld_qkv + h * 64, lane, dq, p.q_scale);
+          }
+        }
       }
     }
   } else if (warp >= 4) {
@@ -379,12 +438,19 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm128, const __grid_const
     c.init();
     while (c.valid(p)) {
       const uint32_t it_now = c.it;
+      if constexpr (DKV) {
+        // EVERY thread waits for the statistics of an item before it may release them, also the warpgroup that
+        // has no step in this item (one step per item when N <= 96): otherwise that warpgroup could arrive on
+        // stat_empty for item it+2 before the other one has arrived for item it, the barrier phase would
+        // complete early, the loader would overwrite statistics still in use and the other warpgroup could
+        // miss a whole phase of stat_full (parity aliasing -> deadlock)
+        if (c.tile == 0 && c.chunk == 0) mbar_wait(&sh->stat_full[c.it & 1], (c.it >> 1) & 1);
+      }
       if ((c.n & 1) == static_cast<uint32_t>(g)) {
         const int row = c.tile * 128 + q * 32 + lane;
         const bool warp_has_rows = c.tile * 128 + q * 32 < p.N;
         uint32_t stat_saddr = 0;
         if constexpr (DKV) {
-          mbar_wait(&sh->stat_full[c.it & 1], (c.it >> 1) & 1);   // returns at once after the first pass
           stat_saddr = smem_u32(sStat + (c.it & 1) * 2 * BW_STAT);
         } else {
           if (stats_tile != static_cast<int>(c.tcount)) {
@@ -478,11 +544,107 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm128, const __grid_const
   }
 }
 
+// ---------------------------------------------------------------------------------------
+// Backward preprocess of the tcgen05 path, one CTA per (sequence, head):
+//   delta[q] = sum_d dO[q, d] * O[q, d]                          (all rows)
+// and, when the odd row N-1 is kept out of the DKV tiles (tail = 1), everything that belongs to KEY N-1:
+//   p[q] = exp(q . k[N-1] - lse[q]),  dS[q] = p[q] (dO[q] . v[N-1] - delta[q])
+//   dV[N-1] = sum_q p[q] dO[q],       dK[N-1] = sum_q dS[q] Q[q]
+// It needs nothing the main kernels produce, so it rides on the pass that reads dO anyway, spread over all
+// SMs (inside the DKV kernel the same work on two spare warps cost more than the third tile it replaced).
+// 8 lanes per row: a row of one head is 128 contiguous bytes -> one 16-byte load per lane and operand.
+// HBM/L2-bound: reads O, dO (+ Q with tail) once.
+// ---------------------------------------------------------------------------------------
+struct AttnDeltaTailParams {
+  const __nv_bfloat16* qkv;
+  const __nv_bfloat16* out;
+  const __nv_bfloat16* d_out;
+  const float* lse;
+  float* delta;
+  __nv_bfloat16* dqkv;
+  long ld_qkv, ld_o;
+  int N, H, D, tail;
+};
+
+__device__ __forceinline__ void unpack8(const uint4& q, float (&v)[8]) {
+  const float2 a = unpack_bf16x2(q.x), b = unpack_bf16x2(q.y), c = unpack_bf16x2(q.z), d = unpack_bf16x2(q.w);
+  v[0] = a.x, v[1] = a.y, v[2] = b.x, v[3] = b.y, v[4] = c.x, v[5] = c.y, v[6] = d.x, v[7] = d.y;
+}
+__device__ __forceinline__ float dot8(const float (&a)[8], const float (&b)[8]) {
+  return ((a[0] * b[0] + a[1] * b[1]) + (a[2] * b[2] + a[3] * b[3])) + ((a[4] * b[4] + a[5] * b[5]) + (a[6] * b[6] + a[7] * b[7]));
+}
+__device__ __forceinline__ float group8_sum(float v) {
+  v += __shfl_xor_sync(0xffffffffu, v, 1);
+  v += __shfl_xor_sync(0xffffffffu, v, 2);
+  v += __shfl_xor_sync(0xffffffffu, v, 4);
+  return v;
+}
+
+constexpr int DT_THREADS = 256;   // 32 row groups of 8 lanes
+
+__global__ void __launch_bounds__(DT_THREADS)
+attn_delta_tail_kernel(const AttnDeltaTailParams p) {
+  __shared__ float red[2][DT_THREADS / 8][64];
+  const int item = blockIdx.x, s = item / p.H, h = item % p.H;
+  const int grp = threadIdx.x >> 3, gl = threadIdx.x & 7;
+  const long row0 = static_cast<long>(s) * p.N;
+  const __nv_bfloat16* o_base = p.out + row0 * p.ld_o + h * 64 + gl * 8;
+  const __nv_bfloat16* do_base = p.d_out + row0 * p.ld_o + h * 64 + gl * 8;
+  const __nv_bfloat16* q_base = p.qkv + row0 * p.ld_qkv + h * 64 + gl * 8;
+  float kt[8], vt[8], acc_v[8], acc_k[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) kt[j] = vt[j] = acc_v[j] = acc_k[j] = 0.f;
+  if (p.tail) {
+    const __nv_bfloat16* t_row = q_base + static_cast<long>(p.N - 1) * p.ld_qkv;
+    unpack8(__ldg(reinterpret_cast<const uint4*>(t_row + p.D)), kt);
+    unpack8(__ldg(reinterpret_cast<const uint4*>(t_row + 2 * p.D)), vt);
+  }
+  for (int q0 = 0; q0 < p.N; q0 += DT_THREADS / 8) {     // warp-uniform trip count (shuffles inside)
+    const int q = q0 + grp;
+    const bool valid = q < p.N;
+    const uint4 zero = make_uint4(0u, 0u, 0u, 0u);
+    float o8[8], d8[8];
+    unpack8(valid ? __ldg(reinterpret_cast<const uint4*>(o_base + q * p.ld_o)) : zero, o8);
+    unpack8(valid ? __ldg(reinterpret_cast<const uint4*>(do_base + q * p.ld_o)) : zero, d8);
+    uint4 qraw = zero;
+    if (p.tail && valid) qraw = __ldg(reinterpret_cast<const uint4*>(q_base + q * p.ld_qkv));
+    const float de = group8_sum(dot8(o8, d8));
+    const long li = static_cast<long>(item) * p.N + (valid ? q : 0);
+    if (gl == 0 && valid) p.delta[li] = de;
+    if (p.tail) {
+      float q8[8];
+      unpack8(qraw, q8);
+      const float sd = group8_sum(dot8(kt, q8));
+      const float dp = group8_sum(dot8(vt, d8));
+      const float pr = valid ? fast_ex2((sd - p.lse[li]) * kLog2eBw) : 0.f;
+      const float ds = pr * (dp - de);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) acc_v[j] = fmaf(pr, d8[j], acc_v[j]), acc_k[j] = fmaf(ds, q8[j], acc_k[j]);
+    }
+  }
+  if (p.tail) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) red[0][grp][gl * 8 + j] = acc_v[j], red[1][grp][gl * 8 + j] = acc_k[j];
+    __syncthreads();
+    if (threadIdx.x < 128) {
+      const int which = threadIdx.x >> 6, c = threadIdx.x & 63;
+      float t = 0.f;
+#pragma unroll 8
+      for (int g = 0; g < DT_THREADS / 8; ++g) t += red[which][g][c];
+      __nv_bfloat16* dst = p.dqkv + (row0 + p.N - 1) * p.ld_qkv + (which == 0 ? 2 * p.D : p.D) + h * 64 + c;
+      *dst = __float2bfloat16(t);
+    }
+  }
+}
+
 // returns 0 if launched, -1 if the shape is not handled here (caller uses the general mma.sync
-// path), > 0 on error.  Expects delta to be filled already.
+// path), > 0 on error.  Fills delta itself (attn_delta_tail_kernel).
 int attention_bwd_tc(const missm_attn_args* a, cudaStream_t stream) {
+  // N <= 96 (one column chunk = one step per item) is declined: the two softmax warpgroups then alternate over
+  // whole ITEMS, and a warpgroup that waits on acc_full only every second phase can see the phase before last
+  // as "its" parity (mbarrier parity aliasing) -- with >= 2 steps per tile the in-order MMA commits exclude that
   const bool ok = !a->causal && a->key_mask == nullptr && a->s_in == 1 && a->tok_stride == 1 &&
-                  a->seq_outer == a->N && a->N <= BW_MAXN && a->N >= 16 && a->head_dim == 64;
+                  a->seq_outer == a->N && a->N <= BW_MAXN && a->N > BW_CW && a->head_dim == 64;
   if (!ok) return -1;
   CUtensorMap tm128, tm16, td128, td16;
   const uint64_t seq_q = static_cast<uint64_t>(a->N) * a->ld_qkv, seq_o = static_cast<uint64_t>(a->N) * a->ld_o;
@@ -493,8 +655,10 @@ int attention_bwd_tc(const missm_attn_args* a, cudaStream_t stream) {
   AttnBwdTcParams p;
   p.N = a->N, p.H = a->H, p.D = a->D, p.n_items = a->n_seq * a->H;
   p.sw = (a->N + 15) / 16 * 16;
-  p.nt = (a->N + 127) / 128;
+  p.tail = attention_tail_enabled(a->N) ? 1 : 0;
+  p.nt = p.tail ? a->N / 128 : (a->N + 127) / 128;
   p.nc = (p.sw + BW_CW - 1) / BW_CW;
+  p.qkv = static_cast<const __nv_bfloat16*>(a->qkv), p.d_out = static_cast<const __nv_bfloat16*>(a->d_out), p.ld_o = a->ld_o;
   p.lse = a->lse, p.delta = a->delta;
   p.dqkv = static_cast<__nv_bfloat16*>(a->dqkv), p.ld_qkv = a->ld_qkv, p.q_scale = a->q_scale;
   const int smem = 4 * BW_RES_BYTES + 4 * BW_TILE_BYTES + 4 * BW_STAT * 4 + 8 * 2048 + static_cast<int>(sizeof(AttnBwdSmem)) + 1024;
@@ -505,6 +669,13 @@ int attention_bwd_tc(const missm_attn_args* a, cudaStream_t stream) {
     configured = true;
   }
   const int grid = p.n_items < persistent_sms() ? p.n_items : persistent_sms();
+  auto launch_delta = [&](int tail) {
+    AttnDeltaTailParams d;
+    d.qkv = p.qkv, d.out = static_cast<const __nv_bfloat16*>(a->out), d.d_out = p.d_out, d.lse = a->lse;
+    d.delta = a->delta, d.dqkv = p.dqkv, d.ld_qkv = a->ld_qkv, d.ld_o = a->ld_o;
+    d.N = a->N, d.H = a->H, d.D = a->D, d.tail = tail;
+    attn_delta_tail_kernel<<<p.n_items, DT_THREADS, 0, stream>>>(d);
+  };
   p.trace = nullptr;
   const char* trace_path = getenv("MISSM_ATTN_TRACE");   // debugging aid: dumps CTA 0's event clocks (synchronises!)
   if (trace_path != nullptr) {
@@ -513,6 +684,8 @@ int attention_bwd_tc(const missm_attn_args* a, cudaStream_t stream) {
     MISSM_CHECK_CUDA(cudaMalloc(&d, nb));
     MISSM_CHECK_CUDA(cudaMemsetAsync(d, 0, nb, stream));
     p.trace = d;
+    launch_delta(0);
+    p.tail = 0, p.nt = (a->N + 127) / 128;     // tracing walks all tiles
     attn_bwd_tc_kernel<true><<<grid, BW_THREADS, smem, stream>>>(tm128, tm16, td128, td16, p);
     p.trace = d + 3 * 330 * 3;
     attn_bwd_tc_kernel<false><<<grid, BW_THREADS, smem, stream>>>(tm128, tm16, td128, td16, p);
@@ -528,7 +701,12 @@ int attention_bwd_tc(const missm_attn_args* a, cudaStream_t stream) {
     cudaFree(d);
     return 0;
   }
-  attn_bwd_tc_kernel<true><<<grid, BW_THREADS, smem, stream>>>(tm128, tm16, td128, td16, p);
+  launch_delta(p.tail);
+  // DKV: its odd KEY row comes from attn_delta_tail_kernel (the kernel only walks the full tiles);
+  // DQ: its odd QUERY row is computed by warps 2-3 of the kernel itself
+  AttnBwdTcParams pk = p;
+  pk.tail = 0;
+  attn_bwd_tc_kernel<true><<<grid, BW_THREADS, smem, stream>>>(tm128, tm16, td128, td16, pk);
   attn_bwd_tc_kernel<false><<<grid, BW_THREADS, smem, stream>>>(tm128, tm16, td128, td16, p);
   MISSM_CHECK_CUDA(cudaGetLastError());
   return 0;

@@ -185,7 +185,7 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   uint32_t spins = 0;
   while (!mbar_try_wait(bar, parity)) {
-    if (++spins > (1u << 26)) {  // try_wait itself sleeps ~us; this is many seconds
+    if (++spins > (1u << 23)) {  // try_wait itself suspends for a while; this is seconds, kernels take < 1 ms
       printf("missm: mbarrier wait timeout (block %d thread %d)\n", blockIdx.x, threadIdx.x);
       __trap();
     }

@@ -157,7 +157,13 @@ def _attn_ref(q, k, v, causal, kmask):
 
 
 @pytest.mark.parametrize("cfg", [(3, 16, 257, False, False), (2, 12, 77, True, True), (2, 16, 593, False, False),
-                                 (5, 4, 8, False, False), (1, 2, 64, True, False), (2, 2, 130, False, True)])
+                                 (5, 4, 8, False, False), (1, 2, 64, True, False), (2, 2, 130, False, True),
+                                 # tcgen05 path: several items per CTA with the odd row on the CUDA cores (257, 129),
+                                 # and shapes without an odd row (256, 272, 200)
+                                 (24, 16, 257, False, False), (40, 8, 129, False, False), (3, 4, 256, False, False),
+                                 (2, 4, 272, False, False), (3, 4, 200, False, False),
+                                 # one step per item and several items per CTA (N <= 96)
+                                 (30, 16, 96, False, False), (40, 16, 64, False, False)])
 def test_attention_fwd_bwd(ops, cfg):
     S, H, N, causal, use_mask = cfg
     torch.manual_seed(N)
@@ -173,6 +179,11 @@ def test_attention_fwd_bwd(ops, cfg):
     ref = _attn_ref(f[0], f[1], f[2], causal, kmask)          # [S,H,N,hd]
     ref_o = ref.permute(0, 2, 1, 3).reshape(S * N, D)
     assert rel(out, ref_o) < 6e-3
+    last = torch.arange(S, device=DEV) * N + N - 1              # the odd row of every sequence, on its own
+    assert rel(out[last], ref_o[last]) < 6e-3
+    if not causal and kmask is None:
+        lse_ref = torch.logsumexp(f[0].detach() @ f[1].detach().transpose(-1, -2), -1)      # [S,H,N]
+        assert (lse - lse_ref).abs().max() < 2e-2
     d_out = (torch.randn(S * N, D, device=DEV)).bfloat16()
     ref_o.backward(d_out.float())
     q_scale = 0.125
@@ -182,6 +193,8 @@ def test_attention_fwd_bwd(ops, cfg):
     assert rel(dqkv[:, :D], gref[:, :D]) < 1.5e-2
     assert rel(dqkv[:, D:2 * D], gref[:, D:2 * D]) < 1.5e-2
     assert rel(dqkv[:, 2 * D:], gref[:, 2 * D:]) < 1.5e-2
+    if N % 128 == 1:                                    # the odd row computed on the CUDA cores
+        assert rel(dqkv[last], gref[last]) < 1.5e-2
     assert rel(dcs, gref.sum(0)) < 1.5e-2               # q/k/v bias gradients
 
 
