@@ -9,6 +9,8 @@
 // mean/variance (biased, as torch), 128-bit loads/stores.
 //   fwd bytes/row : read 4D (+ optional gather), write 2D (bf16 out) or 4D (f32 out) + 8
 //   bwd bytes/row : read 2D|4D (dy) + 4D (x) + 4D (dres, optional), write 4D (+2D bf16 copy)
+#include <cstdlib>
+
 #include "../../include/missm_b200.h"
 #include "missm_common.cuh"
 
@@ -163,6 +165,103 @@ layernorm_bwd_kernel(const void* __restrict__ dy, long lddy, const float* __rest
   }
 }
 
+// The same for wide rows (D >= 768): TWO warps per row, 16 warps per CTA.  With one warp per row a thread carries
+// 3 x D/32 column accumulators plus the row itself (~200 registers for D = 1024): 8 warps per SM, too few loads
+// in flight to cover the HBM latency (measured 4.7 TB/s).  Halving the columns per warp halves the registers, so
+// a 512-thread CTA fits (<= 128 registers) and twice the bytes are in flight.  The two row sums are exchanged
+// through shared memory and a 64-thread named barrier per row pair (double-buffered by iteration parity).
+constexpr int kLn2Warps = 16;
+
+template <int HV, bool DY_BF16>
+__global__ void __launch_bounds__(kLn2Warps * 32, 1)
+layernorm_bwd2_kernel(const void* __restrict__ dy, long lddy, const float* __restrict__ x, long ldx,
+                      const int* __restrict__ row_index, const float* __restrict__ mean,
+                      const float* __restrict__ rstd, const float* __restrict__ gamma,
+                      const float* __restrict__ dres, float* __restrict__ dx,
+                      __nv_bfloat16* __restrict__ dx_bf16, float* __restrict__ partial, int M) {
+  constexpr int D = 2 * HV * 128;
+  constexpr int PAIRS = kLn2Warps / 2;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int pair = warp >> 1, half = warp & 1;
+  const int c0 = half * HV * 32 + lane;          // float4 index of this lane's first column block
+  __shared__ float2 xch[2][PAIRS][2];
+  __shared__ float4 red[kLn2Warps][32];
+  float4 dg[HV], db[HV], ds[HV];
+#pragma unroll
+  for (int i = 0; i < HV; ++i) dg[i] = db[i] = ds[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+  int par = 0;
+  for (int row = blockIdx.x * PAIRS + pair; row < M; row += gridDim.x * PAIRS, par ^= 1) {
+    const long xrow = row_index ? row_index[row] : row;
+    const float mu = mean[row], rs = rstd[row];
+    const float4* xr = reinterpret_cast<const float4*>(x + xrow * ldx);
+    float4 xh[HV], g[HV], r[HV];
+    float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+    for (int i = 0; i < HV; ++i) {     // all loads of the row first
+      xh[i] = xr[c0 + 32 * i];
+      if (dres != nullptr) r[i] = reinterpret_cast<const float4*>(dres + xrow * ldx)[c0 + 32 * i];
+      if constexpr (DY_BF16) {
+        const uint2 pk = reinterpret_cast<const uint2*>(reinterpret_cast<const __nv_bfloat16*>(dy) + row * lddy)[c0 + 32 * i];
+        const float2 a = unpack_bf16x2(pk.x), b = unpack_bf16x2(pk.y);
+        g[i] = make_float4(a.x, a.y, b.x, b.y);
+      } else {
+        g[i] = reinterpret_cast<const float4*>(reinterpret_cast<const float*>(dy) + row * lddy)[c0 + 32 * i];
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < HV; ++i) {
+      const float4 d = g[i];
+      const float4 gmi = __ldg(reinterpret_cast<const float4*>(gamma) + c0 + 32 * i);
+      xh[i] = make_float4((xh[i].x - mu) * rs, (xh[i].y - mu) * rs, (xh[i].z - mu) * rs, (xh[i].w - mu) * rs);
+      g[i] = make_float4(d.x * gmi.x, d.y * gmi.y, d.z * gmi.z, d.w * gmi.w);
+      s1 += (g[i].x + g[i].y) + (g[i].z + g[i].w);
+      s2 += (g[i].x * xh[i].x + g[i].y * xh[i].y) + (g[i].z * xh[i].z + g[i].w * xh[i].w);
+      dg[i].x += d.x * xh[i].x, dg[i].y += d.y * xh[i].y, dg[i].z += d.z * xh[i].z, dg[i].w += d.w * xh[i].w;
+      db[i].x += d.x, db[i].y += d.y, db[i].z += d.z, db[i].w += d.w;
+    }
+    s1 = warp_sum(s1), s2 = warp_sum(s2);
+    if (lane == 0) xch[par][pair][half] = make_float2(s1, s2);
+    asm volatile("bar.sync %0, 64;" ::"r"(1 + pair) : "memory");
+    const float2 other = xch[par][pair][half ^ 1];
+    const float c1 = (s1 + other.x) * (1.0f / D), c2 = (s2 + other.y) * (1.0f / D);
+#pragma unroll
+    for (int i = 0; i < HV; ++i) {
+      float4 o;
+      o.x = rs * (g[i].x - c1 - xh[i].x * c2);
+      o.y = rs * (g[i].y - c1 - xh[i].y * c2);
+      o.z = rs * (g[i].z - c1 - xh[i].z * c2);
+      o.w = rs * (g[i].w - c1 - xh[i].w * c2);
+      if (dres != nullptr) o.x += r[i].x, o.y += r[i].y, o.z += r[i].z, o.w += r[i].w;
+      reinterpret_cast<float4*>(dx + xrow * ldx)[c0 + 32 * i] = o;
+      ds[i].x += o.x, ds[i].y += o.y, ds[i].z += o.z, ds[i].w += o.w;
+      if (dx_bf16 != nullptr)
+        reinterpret_cast<uint2*>(dx_bf16 + xrow * ldx)[c0 + 32 * i] =
+            make_uint2(pack_bf16x2(o.x, o.y), pack_bf16x2(o.z, o.w));
+    }
+  }
+
+  // block reduction over the row pairs, per column half
+  float* pg = partial + static_cast<long>(blockIdx.x) * 3 * D;
+#pragma unroll 1
+  for (int which = 0; which < 3; ++which) {
+#pragma unroll 1
+    for (int i = 0; i < HV; ++i) {
+      red[warp][lane] = which == 0 ? dg[i] : (which == 1 ? db[i] : ds[i]);
+      __syncthreads();
+      if (warp < 2) {
+        float4 a = red[warp][lane];
+#pragma unroll
+        for (int w = 1; w < PAIRS; ++w) {
+          const float4 b = red[2 * w + warp][lane];
+          a.x += b.x, a.y += b.y, a.z += b.z, a.w += b.w;
+        }
+        reinterpret_cast<float4*>(pg + which * D)[c0 + 32 * i] = a;
+      }
+      __syncthreads();
+    }
+  }
+}
+
 // out[c] = sum_r partial[r][c]    (deterministic second stage of column reductions)
 // block = 32 columns x 8 row-threads: coalesced 128 B row segments, fixed summation order
 __global__ void __launch_bounds__(256)
@@ -214,13 +313,28 @@ static int launch_ln_bwd(int vec, int grid, cudaStream_t st, const void* dy, lon
     layernorm_bwd_kernel<V, DY_BF16><<<grid, kLnWarps * 32, 0, st>>>(                      \
         dy, lddy, x, ldx, ridx, mean, rstd, gamma, dres, dx, dxb, partial, M);             \
     break;
-  switch (vec) {
-    LN_CASE(1) LN_CASE(2) LN_CASE(3) LN_CASE(4) LN_CASE(5) LN_CASE(6) LN_CASE(8) LN_CASE(10)
-    LN_CASE(12)
-    default:
-      MISSM_REQUIRE(false, "layernorm: unsupported width %d", vec * 128);
+#define LN2_CASE(V)                                                                        \
+  case V:                                                                                  \
+    layernorm_bwd2_kernel<V / 2, DY_BF16><<<grid, kLn2Warps * 32, 0, st>>>(                \
+        dy, lddy, x, ldx, ridx, mean, rstd, gamma, dres, dx, dxb, partial, M);             \
+    break;
+  static const bool one_warp_rows = getenv("MISSM_LN_BWD_1WARP") != nullptr;   // A/B switch
+  if ((vec == 6 || vec == 8) && !one_warp_rows) {
+    switch (vec) {
+      LN2_CASE(6) LN2_CASE(8)
+      default:
+        MISSM_REQUIRE(false, "layernorm: unsupported width %d", vec * 128);
+    }
+  } else {
+    switch (vec) {
+      LN_CASE(1) LN_CASE(2) LN_CASE(3) LN_CASE(4) LN_CASE(5) LN_CASE(6) LN_CASE(8) LN_CASE(10)
+      LN_CASE(12)
+      default:
+        MISSM_REQUIRE(false, "layernorm: unsupported width %d", vec * 128);
+    }
   }
 #undef LN_CASE
+#undef LN2_CASE
   MISSM_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
