@@ -220,11 +220,11 @@ def run_gpu_arm(a):
         return loss
 
     def step_e2e():
+        # the call a user makes, with HOST buffers: finetune_model.forward(pinned host tensors, host missing_index);
+        # every tower uploads its own input on its own stream (bank.LanguageBind.forward), the loss comes back
         net.zero_grad(set_to_none=True)
-        d = {m: {'pixel_values': v['pixel_values'].to(dev, non_blocking=True)} for m, v in host.items()}
-        m_ = mi_host.to(dev, non_blocking=True)
         l_ = labels_host.to(dev, non_blocking=True)
-        loss = crit(net(d, m_), l_)
+        loss = crit(net(host, mi_host), l_)
         loss.backward()
         return float(loss)                                     # device -> host read of the step's result
 

@@ -10,7 +10,8 @@
  *   - every pointer is a DEVICE pointer unless the name ends in _host;
  *   - `stream` is a cudaStream_t passed as void*; nothing synchronises, nothing allocates
  *     device memory, there is no global mutable state besides the last-error string
- *     (thread-local), so calls are re-entrant (autograd worker threads);
+ *     (thread-local) and the persistent-grid size (missm_set_persistent_sms), so calls are
+ *     re-entrant (autograd worker threads);
  *   - return value 0 = ok; non-zero = error, text in missm_last_error();
  *   - bf16 tensors are row-major with the stated leading dimension in ELEMENTS.
  */
@@ -27,6 +28,12 @@ extern "C" {
 
 int missm_version(void);
 const char* missm_last_error(void);
+
+/* SMs the persistent kernels (tcgen05 GEMM, tcgen05 attention: one CTA per SM) spread over from now on; n <= 0
+ * restores the default (148, or MISSM_PERSISTENT_SMS).  Process-wide, read at every launch.  The host side lowers it
+ * for the backward pass under data parallelism so that NCCL's all-reduce CTAs (issued by the unchanged script's DDP
+ * wrapper, train_ddp.py:189) find free SMs instead of queueing behind kernels that own whole SMs. */
+int missm_set_persistent_sms(int32_t n);
 
 /* ---------------------------------------------------------------------------------------
  * tcgen05 GEMM:  C[m,n] = epilogue( sum_k A[m,k] * B[n,k] )     bf16 in, fp32 accumulate

@@ -18,6 +18,8 @@
 #include <cstdio>
 #include <cstring>
 
+#include <atomic>
+
 #include "../../include/missm_b200.h"
 #include "gemm_common.cuh"
 #include "missm_common.cuh"
@@ -213,6 +215,8 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA,
 // ---------------------------------------------------------------------------------------
 static thread_local char g_last_error[512] = "";
 
+static std::atomic<int> g_persistent_sms_override{0};
+
 int persistent_sms() {
   static const int v = [] {
     const char* e = getenv("MISSM_PERSISTENT_SMS");
@@ -220,7 +224,8 @@ int persistent_sms() {
     if (n < 2 || n > kNumSMs) n = kNumSMs;
     return n & ~1;
   }();
-  return v;
+  const int o = g_persistent_sms_override.load(std::memory_order_relaxed);
+  return o > 0 && o < v ? o : v;
 }
 
 void set_last_error(const char* fmt, ...) {
@@ -332,6 +337,11 @@ using namespace missm;
 
 extern "C" int missm_version(void) { return MISSM_ABI_VERSION; }
 extern "C" const char* missm_last_error(void) { return g_last_error; }
+extern "C" int missm_set_persistent_sms(int32_t n) {
+  if (n < 2 || n > kNumSMs) n = 0;
+  g_persistent_sms_override.store(n & ~1, std::memory_order_relaxed);
+  return 0;
+}
 
 extern "C" int missm_gemm_bf16(const missm_gemm_args* a, void* stream_v) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_v);

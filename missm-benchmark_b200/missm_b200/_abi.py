@@ -36,6 +36,7 @@ SIGNATURES = {
     "missm_gather_rows": [P, P, P, I, L, P],
     "missm_fusion_sum_fwd": [P, P],
     "missm_fusion_sum_bwd": [P, P, P, P, P, P],
+    "missm_set_persistent_sms": [I],
 }
 # exported but with non-standard return types / no args
 OTHER_EXPORTS = ["missm_version", "missm_last_error"]

@@ -302,3 +302,19 @@ class ScatterZeroFn(torch.autograd.Function):
     def backward(ctx, d_out):
         (present_idx,) = ctx.saved_tensors
         return ops.gather_rows(_contig(d_out), present_idx, ctx.n), None, None, None, None
+
+
+# ------------------------------------------------------------------------------------------
+# data parallelism: the first backward node of a tower shrinks the persistent grids, so that the
+# all-reduce kernels DDP launches while the backward is still running find free SMs
+# ------------------------------------------------------------------------------------------
+class BackwardSmsFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, n_sms):
+        ctx.n_sms = n_sms
+        return x.view_as(x)
+
+    @staticmethod
+    def backward(ctx, g):
+        ops.set_persistent_sms(ctx.n_sms)
+        return g, None

@@ -26,6 +26,20 @@ model_dict = {
 }
 
 
+def _ddp_backward_sms():
+    """Optional policy for data parallelism (MISSM_DDP_SMS=n, default off): during the BACKWARD pass the persistent
+    kernels spread over n SMs only, leaving the rest to the all-reduce CTAs DDP launches while the backward is
+    still running (a one-CTA-per-SM grid owns every SM's registers and shared memory, so an NCCL CTA can only
+    start when a whole GEMM ends, and the next GEMM then runs with late CTAs).  Measured at 2 x B200, ms / step:
+    off 117.0-117.2; 132 SMs for the whole step + NCCL_MAX_NCHANNELS=16 113.5; 132 in the backward only 116.5;
+    124: 119.0; 140: 119.7; 144 + 4 channels 129.8 (all-reduce too slow).  Within run-to-run noise of one
+    another, hence off by default; a dynamic tile scheduler is the real fix."""
+    import torch.distributed as dist
+    if not (dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1):
+        return 0
+    return int(os.environ.get("MISSM_DDP_SMS", "0"))
+
+
 class _ZeroTower(torch.autograd.Function):
     """A tower that saw zero present samples on this rank still has to hand DDP a gradient for
     every parameter (find_unused_parameters=False, train_ddp.py:189): emit zero embeddings whose
@@ -96,6 +110,10 @@ class LanguageBind(nn.Module):
             pool[key] = [torch.cuda.Stream(device=device) for _ in range(n)]
         return pool[key]
 
+    def _param_device(self):
+        p = next(self.parameters(), None)
+        return p.device if p is not None else torch.device('cpu')
+
     def _scale(self, key):
         if self.use_temp and key != 'language':
             return float(self.modality_scale[key].detach().exp())
@@ -106,13 +124,22 @@ class LanguageBind(nn.Module):
         `missing_index` (int64 [B], optional) enables compaction: a tower only runs the samples whose
         code differs from its own; rows of missing samples come back as zeros."""
         ag.reset_side_channel()
+        ddp_sms = _ddp_backward_sms() if torch.is_grad_enabled() else 0
+        if ddp_sms:
+            ops.set_persistent_sms(0)          # forward: no all-reduce in flight, all SMs
         keys = list(inputs.keys())
         plan = {}
+        # HOST inputs are accepted when the model lives on a CUDA device: every tower uploads its own tensors on
+        # its own stream (pinned memory -> asynchronous), so the copy of tower k+1 overlaps the compute of tower k.
+        # The caller must not overwrite a pinned buffer before the step's result has been read back.
+        mdev = self._param_device()
         if missing_index is not None and self.compaction and len(keys) > 0:
             mi = missing_index.reshape(-1).to(torch.int64).contiguous()
             if not mi.is_cuda:
-                raise RuntimeError("missm_b200: missing_index is on the CPU; the B200 path has no CPU fallback "
-                                   "(move the model and its inputs to a CUDA device)")
+                if mdev.type != 'cuda':
+                    raise RuntimeError("missm_b200: missing_index is on the CPU; the B200 path has no CPU fallback "
+                                       "(move the model and its inputs to a CUDA device)")
+                mi = mi.to(mdev, non_blocking=True)
             codes = [MISSING_TYPE_INDEX.get(k, -1) for k in keys]
             idx, slot, counts = ops.compact_mask(mi, codes)
             counts = counts.tolist()          # the one host sync of the step: sizes of the towers' batches
@@ -121,7 +148,7 @@ class LanguageBind(nn.Module):
                 if counts[i] < B:
                     plan[k] = (idx[i], slot[i], counts[i], B)
         outputs = {}
-        dev = None
+        dev = mdev if mdev.type == 'cuda' else None
         for v in inputs.values():
             for t in v.values():
                 if torch.is_tensor(t) and t.is_cuda:
@@ -139,6 +166,9 @@ class LanguageBind(nn.Module):
             else:
                 ctx = contextlib.nullcontext()
             with ctx:
+                if mdev.type == 'cuda':
+                    value = {k: (t.to(mdev, non_blocking=True) if torch.is_tensor(t) and not t.is_cuda else t)
+                             for k, t in value.items()}
                 if key in plan:
                     pidx, slot, n, B = plan[key]
                     if n == 0:
@@ -149,6 +179,8 @@ class LanguageBind(nn.Module):
                         outputs[key] = ag.ScatterZeroFn.apply(y, slot, pidx, n, B)
                 else:
                     outputs[key] = enc(**value, proj=proj, scale=scale)[1]
+                if ddp_sms and outputs[key].requires_grad:
+                    outputs[key] = ag.BackwardSmsFn.apply(outputs[key], ddp_sms)
             if use_streams:
                 outputs[key].record_stream(main)
         if use_streams:

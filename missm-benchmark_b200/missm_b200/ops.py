@@ -20,6 +20,11 @@ LAUNCHES = [0]
 GEMM_TIMING = None
 
 
+def set_persistent_sms(n):
+    """SMs the persistent kernels use from now on (n <= 0: default).  See include/missm_b200.h."""
+    check(lib().missm_set_persistent_sms(int(n)), "set_persistent_sms")
+
+
 def _p(t):
     return ctypes.c_void_p(t.data_ptr()) if t is not None else None
 

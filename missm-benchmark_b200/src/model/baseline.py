@@ -258,6 +258,11 @@ class finetune_model(nn.Module):
         self.fusion = _FUSIONS[args.fusion_type](args, output_dims)
 
     def forward(self, data, missing_index):
+        # host inputs: the bank uploads every tower's tensors on that tower's stream; missing_index goes up once
+        if torch.is_tensor(missing_index) and not missing_index.is_cuda:
+            p = next(self.parameters(), None)
+            if p is not None and p.is_cuda:
+                missing_index = missing_index.to(p.device, non_blocking=True)
         # `retrieval` ignores missing_index (the loader substituted a same-label sample and reset the
         # code to 0, data_loader.py:271-276), so nothing may be skipped for it
         if getattr(self.encoder, 'supports_compaction', False) and self.fusion_type != 'retrieval':

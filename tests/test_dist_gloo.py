@@ -27,7 +27,8 @@ def _free_port():
 def _worker(rank, world, port, q):
     sys.path.insert(0, os.path.join(ROOT, "missm-benchmark_b200"))
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
-    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world),
+                      MISSM_DDP_SMS="132")
     dist.init_process_group("gloo", rank=rank, world_size=world)
     from missm_b200 import dist_utils
     import restatement as R
@@ -36,6 +37,11 @@ def _worker(rank, world, port, q):
     out["max"] = dist_utils.max_over_ranks(10.0 + rank)
     mi = R.synth_missing_index(64, 0.3, ['image', 'depth', 'thermal'], seed=dist_utils.rank_seed(2025, rank))
     out["missing"] = mi.tolist()
+    # optional data-parallel policy of the bank (MISSM_DDP_SMS): the backward pass leaves SMs to NCCL, and the
+    # all-reduce gets no more channels than that (set at package import: WORLD_SIZE > 1 is in the environment)
+    from missm_b200.bank import _ddp_backward_sms
+    out["ddp_sms"] = _ddp_backward_sms()
+    out["nccl_channels"] = os.environ.get("NCCL_MAX_NCHANNELS")
     # DDP over a (pure torch) fusion head on CPU: grads must be identical on both ranks afterwards
     torch.manual_seed(0)
     args = types.SimpleNamespace(modality_types=['image', 'audio'], feature_dims=16, fusion_dim=8, dropout_prob=0.0)
@@ -66,6 +72,7 @@ def test_two_rank_host_logic():
     assert res[0]["max"] == res[1]["max"] == 11.0
     assert res[0]["missing"] != res[1]["missing"] and sum(1 for v in res[0]["missing"] if v) == 19
     assert res[0]["all_have_grad"] and res[1]["all_have_grad"]
+    assert res[0]["ddp_sms"] == res[1]["ddp_sms"] == 132 and res[0]["nccl_channels"] == "16"
     for n in res[0]["grads"]:
         assert torch.allclose(torch.tensor(res[0]["grads"][n]), torch.tensor(res[1]["grads"][n])), n
 

@@ -145,6 +145,29 @@ def test_compaction_matches_full_batch(tiny):
     assert max(dg) == 0.0
 
 
+def test_host_inputs_match_device_inputs(tiny):
+    """finetune_model.forward(pinned HOST tensors, host missing_index) -- the end-to-end call bench.py times --
+    uploads every tower's input on that tower's stream; results must be identical to device-resident inputs."""
+    meta = tiny['meta']
+    modal_types = ['image', 'depth', 'thermal']
+    model, cfgs, tcfg, _ = make(meta, modal_types, 'sum')
+    model.train()
+    B = 8
+    host = R.synth_inputs(modal_types, B, cfgs, tcfg, seed=5)
+    host = {m: {k: t.pin_memory() for k, t in v.items()} for m, v in host.items()}
+    mi_host = torch.tensor([0, 4, 5, 6, 4, 0, 6, 0]).pin_memory()
+    out_h = model(host, mi_host)
+    out_h.sum().backward()
+    g_h = {n: p.grad.clone() for n, p in model.named_parameters() if p.grad is not None}
+    model.zero_grad(set_to_none=True)
+    out_d = model(to_dev(host), mi_host.to(DEV))
+    out_d.sum().backward()
+    assert torch.equal(out_h, out_d)
+    for n, p in model.named_parameters():
+        if p.grad is not None:
+            assert rel(g_h[n], p.grad) < 1e-5, n       # split-K wgrad atomics reorder fp32 sums, nothing else differs
+
+
 @pytest.mark.skipif(not os.path.exists(os.path.join(GOLD, "config1_full.pt")), reason="full golden not generated")
 def test_config1_full_size_matches_reference_golden():
     """BASELINE.json config 1: ViT-L/14 224 image tower + text tower + sum head, B = 8, one
