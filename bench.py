@@ -200,7 +200,12 @@ def run_gpu_arm(a):
     model.train()
     net = model
     if world > 1:
-        net = torch.nn.parallel.DistributedDataParallel(model, device_ids=[local])   # train_ddp.py:189
+        # train_ddp.py:189 (broadcast_buffers=True, find_unused_parameters=False, default gradient copies).
+        # MISSM_BENCH_BUCKET_VIEW=1 is a measurement switch only (gradient_as_bucket_view=True: no per-parameter
+        # copies into / out of the all-reduce buckets), reported in config.ddp
+        bucket_view = os.environ.get("MISSM_BENCH_BUCKET_VIEW") is not None
+        net = torch.nn.parallel.DistributedDataParallel(model, device_ids=[local], broadcast_buffers=True,
+                                                        find_unused_parameters=False, gradient_as_bucket_view=bucket_view)
 
     B = a.batch
     host = R.synth_inputs(MODALS, B, cfgs, tcfg, seed=rank)
@@ -226,7 +231,7 @@ def run_gpu_arm(a):
         l_ = labels_host.to(dev, non_blocking=True)
         loss = crit(net(host, mi_host), l_)
         loss.backward()
-        return float(loss)                                     # device -> host read of the step's result
+        return float(loss.detach())                            # device -> host read of the step's result
 
     def barrier():
         if world > 1:
@@ -313,6 +318,8 @@ def run_gpu_arm(a):
             "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
             "config": {"workload": WORKLOAD, "batch_per_gpu": B, "missing_ratio": a.missing,
                        "missing_samples": n_missing, "fusion": "sum", "layers": a.layers, "tower_streams": bool(model.encoder.tower_streams),
+                       "ddp": (None if world == 1 else "DistributedDataParallel as train_ddp.py:189" +
+                               (" + gradient_as_bucket_view (measurement switch)" if os.environ.get("MISSM_BENCH_BUCKET_VIEW") else "")),
                        "host_issue_ms_per_step": host_issue_ms,
                        "step": "zero_grad + forward + CrossEntropy + backward (DDP allreduce at N>1); optimizer excluded (metric is fwd+bwd)",
                        "l2": "working set >> 126 MB L2 every step (1.8 GB bf16 weights + >30 GB activations)",
