@@ -16,7 +16,16 @@
 //   warp 2 : TMEM allocator (cta_group::2, both CTAs)
 //   warps 4..11 : epilogue, each CTA drains its own 128 accumulator rows (same fused epilogues as the
 //                 1-CTA kernel); "accumulator free" arrives on the leader's barrier across the cluster
+// Tile schedule: DYNAMIC through Blackwell's cluster launch control (CLC).  The grid holds one cluster per work
+// unit; the clusters that are resident (74 when the GPU is idle) process their own unit and then keep cancelling
+// clusters that have not started yet (clusterlaunchcontrol.try_cancel, response multicast into both CTAs'
+// shared memory, ~320 cycles) and take over their units.  A pair that starts late -- because another tower's
+// kernel, or an NCCL all-reduce CTA, still holds its SMs -- simply processes fewer tiles instead of stretching
+// the kernel by a whole tile time as the static "tile = pair + i * pairs" walk does (kept for stream-K and for
+// capped grids, MISSM_GEMM_STATIC=1 forces it).
 // Bound: tensor pipe.  Algorithmic work per launch = 2*M*N*K flop.
+#include <cstdlib>
+
 #include "../../include/missm_b200.h"
 #include "gemm_common.cuh"
 #include "missm_common.cuh"
@@ -29,11 +38,60 @@ struct Gemm2Cfg {
   static constexpr int STAGE_BYTES = A_STAGE_BYTES + B_HALF_BYTES;
   static constexpr int STAGES = (BN == 256) ? 6 : 8;
   static constexpr int TMEM_COLS = 2 * BN;
-  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers + tmem slot*/ +
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align*/ + 512 /*barriers, tmem slot, tile feed*/ +
                                     kEpiWarps * kEpiStageBytes /*epilogue staging*/;
 };
 
-template <int BN, int EPI, bool OUT_F32>
+// ---------------------------------------------------------------------------------------
+// The tile feed of one CTA: the producer warp obtains work units (statically or from CLC) and publishes them to
+// the other roles of ITS CTA through a 4-deep ring + mbarriers; -1 ends the kernel.
+// ---------------------------------------------------------------------------------------
+struct TileFeedSmem {
+  uint4 clc_resp;              // CLC response (written by hardware into both CTAs of the pair)
+  uint64_t clc_bar;            // ... completes 16 transaction bytes on this barrier, in every CTA
+  uint64_t peer_armed;         // leader's copy: the peer has armed clc_bar and is done with the previous response
+  uint64_t full[4], empty[4];
+  int ring[4];
+};
+
+__device__ __forceinline__ void clc_try_cancel(const uint4* resp, const uint64_t* bar) {
+  asm volatile(
+      "clusterlaunchcontrol.try_cancel.async.shared::cta.mbarrier::complete_tx::bytes.multicast::cluster::all.b128 [%0], [%1];"
+      ::"r"(smem_u32(resp)), "r"(smem_u32(bar)) : "memory");
+}
+// -> first CTA id (x) of the cancelled cluster, or -1 if nothing was left to cancel
+__device__ __forceinline__ int clc_decode(const uint4* resp) {
+  uint32_t valid = 0, x = 0, y, z;
+  asm volatile(
+      "{\n.reg .pred p1;\n.reg .b128 r;\nld.shared.b128 r, [%4];\n"
+      "clusterlaunchcontrol.query_cancel.is_canceled.pred.b128 p1, r;\nselp.u32 %3, 1, 0, p1;\n"
+      "@p1 clusterlaunchcontrol.query_cancel.get_first_ctaid.v4.b32.b128 {%0, %1, %2, _}, r;\n}\n"
+      : "=r"(x), "=r"(y), "=r"(z), "=r"(valid) : "r"(smem_u32(resp)) : "memory");
+  (void)y, (void)z;
+  return valid ? static_cast<int>(x) : -1;
+}
+__device__ __forceinline__ void mbar_arrive_release_cluster(uint32_t cluster_addr) {
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+// consumer side of the ring (whole warp calls; one lane releases the slot)
+__device__ __forceinline__ int feed_take(TileFeedSmem* f, uint32_t& it) {
+  const int slot = it & 3;
+  mbar_wait(&f->full[slot], (it >> 2) & 1);
+  const int w = *reinterpret_cast<volatile int*>(&f->ring[slot]);
+  __syncwarp();
+  if (lane_id() == 0) mbar_arrive(&f->empty[slot]);
+  ++it;
+  return w;
+}
+// linear work unit -> tile (n fastest) and k-block range
+__device__ __forceinline__ void unit_decode(const GemmParams& p, int w, int& tile, int& kb0, int& kb1) {
+  const int tiles_mn = p.num_m_blk * p.num_n_blk;
+  tile = w % tiles_mn;
+  kb0 = (w / tiles_mn) * p.kblk_per_split;
+  kb1 = kb0 + p.kblk_per_split < p.num_kblk ? kb0 + p.kblk_per_split : p.num_kblk;
+}
+
+template <int BN, int EPI, bool OUT_F32, bool CLC>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kGemmThreads, 1)
 gemm_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                          const GemmParams p) {
@@ -50,7 +108,8 @@ gemm_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
   uint64_t* tfull_bar = empty_bar + STAGES;
   uint64_t* tempty_bar = tfull_bar + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
-  uint8_t* sStage = reinterpret_cast<uint8_t*>(full_bar) + 256;   // kEpiWarps x 4 KB epilogue staging
+  TileFeedSmem* feed = reinterpret_cast<TileFeedSmem*>(reinterpret_cast<uint8_t*>(full_bar) + 256);   // 16-byte aligned
+  uint8_t* sStage = reinterpret_cast<uint8_t*>(full_bar) + 512;   // kEpiWarps x 4 KB epilogue staging
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t rank = cluster_ctarank();          // 0 = leader
@@ -68,6 +127,14 @@ gemm_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tfull_bar[i], 1);
       mbar_init(&tempty_bar[i], 2 * kEpiWarps);   // leader's copy: epilogue warps of BOTH CTAs
+    }
+    if constexpr (CLC) {
+      mbar_init(&feed->clc_bar, 1);
+      mbar_init(&feed->peer_armed, 1);
+      for (int i = 0; i < 4; ++i) {
+        mbar_init(&feed->full[i], 1);
+        mbar_init(&feed->empty[i], kEpiWarps + (cluster_ctarank() == 0 ? 1 : 0));   // epilogue warps (+ MMA warp)
+      }
     }
     fence_mbar_init();
   }
@@ -88,7 +155,23 @@ gemm_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
     uint32_t phase = 0;
     GemmWork work(p, pair, num_pairs);
     int tile, kb0, kb1;
-    while (work.next(tile, kb0, kb1)) {
+    int unit = pair;          // CLC: this cluster's own unit first
+    uint32_t fit = 0;
+    while (true) {
+      if constexpr (CLC) {
+        // publish the unit (or the end marker) to the other roles of this CTA
+        const int slot = fit & 3;
+        mbar_wait(&feed->empty[slot], ((fit >> 2) & 1) ^ 1);
+        if (elect_one_sync()) {
+          *reinterpret_cast<volatile int*>(&feed->ring[slot]) = unit;
+          mbar_arrive(&feed->full[slot]);
+        }
+        __syncwarp();
+        if (unit < 0) break;
+        unit_decode(p, unit, tile, kb0, kb1);
+      } else {
+        if (!work.next(tile, kb0, kb1)) break;
+      }
       const int m_blk = tile / p.num_n_blk, n_blk = tile % p.num_n_blk;
       const int m0 = m_blk * 256 + static_cast<int>(rank) * 128;
       const int n0 = n_blk * BN + static_cast<int>(rank) * (BN / 2);
@@ -115,6 +198,26 @@ gemm_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
         __syncwarp();
         if (++stage == STAGES) stage = 0, phase ^= 1;
       }
+      if constexpr (CLC) {
+        // next unit: cancel a cluster that has not started yet and take its place.  Every CTA arms its own
+        // barrier; the leader queries once the peer has armed (and therefore finished reading the previous
+        // response, which the multicast write is about to replace)
+        if (elect_one_sync()) {
+          mbar_arrive_expect_tx(&feed->clc_bar, 16);
+          if (rank != 0) mbar_arrive_release_cluster(mapa_shared(smem_u32(&feed->peer_armed), 0));
+        }
+        __syncwarp();
+        if (rank == 0) {
+          mbar_wait(&feed->peer_armed, fit & 1);
+          if (elect_one_sync()) clc_try_cancel(&feed->clc_resp, &feed->clc_bar);
+          __syncwarp();
+        }
+        mbar_wait(&feed->clc_bar, fit & 1);
+        const int first_cta = clc_decode(&feed->clc_resp);
+        fence_proxy_async_smem();      // this read is ordered before the next asynchronous write of the response
+        unit = first_cta < 0 ? -1 : first_cta >> 1;
+        ++fit;
+      }
     }
   } else if (warp == 1) {
     // ================================ MMA issuer (leader only) ========================
@@ -130,7 +233,15 @@ gemm_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
       uint32_t acc_phase = 0;
       GemmWork work(p, pair, num_pairs);
       int tile, kb0, kb1;
-      while (work.next(tile, kb0, kb1)) {
+      uint32_t fit = 0;
+      while (true) {
+        if constexpr (CLC) {
+          const int unit = feed_take(feed, fit);
+          if (unit < 0) break;
+          unit_decode(p, unit, tile, kb0, kb1);
+        } else {
+          if (!work.next(tile, kb0, kb1)) break;
+        }
         mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + acc * BN;
@@ -162,7 +273,15 @@ gemm_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
     uint32_t acc_phase = 0;
     GemmWork work(p, pair, num_pairs);
     int tile, kb0, kb1;
-    while (work.next(tile, kb0, kb1)) {
+    uint32_t fit = 0;
+    while (true) {
+      if constexpr (CLC) {
+        const int unit = feed_take(feed, fit);
+        if (unit < 0) break;
+        unit_decode(p, unit, tile, kb0, kb1);
+      } else {
+        if (!work.next(tile, kb0, kb1)) break;
+      }
       const int m_blk = tile / p.num_n_blk, n_blk = tile % p.num_n_blk;
       const int row0 = m_blk * 256 + static_cast<int>(rank) * 128 + q * 32;
       // in-place RESID (aux_in aliases C): this warp's tile is only ever touched by this warp, and its
@@ -204,11 +323,11 @@ gemm_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
   }
 }
 
-template <int BN, int EPI, bool OUT_F32>
-static int launch_gemm2(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmParams& p, int grid,
-                        cudaStream_t stream) {
+template <int BN, int EPI, bool OUT_F32, bool CLC>
+static int launch_gemm2_sched(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmParams& p, int grid,
+                              cudaStream_t stream) {
   using Cfg = Gemm2Cfg<BN>;
-  auto kern = gemm_tcgen05_2cta_kernel<BN, EPI, OUT_F32>;
+  auto kern = gemm_tcgen05_2cta_kernel<BN, EPI, OUT_F32, CLC>;
   static bool configured = false;  // benign race: the attribute call is idempotent
   if (!configured) {
     MISSM_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
@@ -217,6 +336,13 @@ static int launch_gemm2(const CUtensorMap& tmA, const CUtensorMap& tmB, const Ge
   kern<<<grid, kGemmThreads, Cfg::SMEM_BYTES, stream>>>(tmA, tmB, p);
   MISSM_CHECK_CUDA(cudaGetLastError());
   return 0;
+}
+// grid < 0: dynamic schedule, one cluster per work unit (-grid CTAs)
+template <int BN, int EPI, bool OUT_F32>
+static int launch_gemm2(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmParams& p, int grid,
+                        cudaStream_t stream) {
+  if (grid < 0) return launch_gemm2_sched<BN, EPI, OUT_F32, true>(tmA, tmB, p, -grid, stream);
+  return launch_gemm2_sched<BN, EPI, OUT_F32, false>(tmA, tmB, p, grid, stream);
 }
 
 template <int BN>
@@ -309,7 +435,10 @@ int gemm_launch_2cta(const missm_gemm_args* a, GemmParams p, cudaStream_t stream
     rc = make_tmap_2d_bf16(&tmB, a->B, a->N, a->K, a->ldb, 64, BK);
   if (rc) return rc;
 
-  const int grid = 2 * grid_pairs;
+  // dynamic (CLC) schedule unless stream-K, a capped grid (the cap exists to keep SMs free) or the A/B switch
+  static const bool force_static = getenv("MISSM_GEMM_STATIC") != nullptr;
+  const bool dynamic = !force_static && !p.stream_k && kPairs == kNumSMs / 2 && work > grid_pairs;
+  const int grid = dynamic ? -2 * static_cast<int>(work) : 2 * grid_pairs;
   if (bn == 256) return dispatch_epi2<256>(a->epilogue, a->out_f32 != 0, tmA, tmB, p, grid, stream);
   return dispatch_epi2<128>(a->epilogue, a->out_f32 != 0, tmA, tmB, p, grid, stream);
 }
