@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define MISSM_ABI_VERSION 2
+#define MISSM_ABI_VERSION 3   /* 3: missm_set_persistent_sms */
 
 int missm_version(void);
 const char* missm_last_error(void);
