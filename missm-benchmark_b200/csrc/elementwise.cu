@@ -88,8 +88,11 @@ reduce_rows_kernel(const float* __restrict__ partial, int R, int N, float* __res
 // patch extraction (im2col of a stride = kernel conv):  pixels f32 [B, C, H, W] ->
 // patches bf16 [B * gh * gw, Kpad], column k = (c * ps + i) * ps + j  (Conv2d weight order)
 // ---------------------------------------------------------------------------------------
+__device__ __forceinline__ void patch_store(__nv_bfloat16* p, float v) { *p = __float2bfloat16(v); }
+__device__ __forceinline__ void patch_store(float* p, float v) { *p = v; }
+template <typename OutT>
 __global__ void patchify_kernel(const float* __restrict__ px, const int* __restrict__ sample_index,
-                                __nv_bfloat16* __restrict__ out, int Bn, int C, int T, int H, int W,
+                                OutT* __restrict__ out, int Bn, int C, int T, int H, int W,
                                 int ps, int gh, int gw, int Kpad) {
   // one warp per (sample, channel, pixel row): reads W contiguous floats (coalesced)
   const int lane = threadIdx.x & 31;
@@ -108,7 +111,7 @@ __global__ void patchify_kernel(const float* __restrict__ px, const int* __restr
     for (int xcol = lane; xcol < gw * ps; xcol += 32) {
       const int pxi = xcol / ps, j = xcol % ps;
       const long prow = ((static_cast<long>(b) * T + t) * gh + py) * gw + pxi;
-      out[prow * Kpad + (c * ps + i) * ps + j] = __float2bfloat16(row[xcol]);
+      patch_store(out + prow * Kpad + (c * ps + i) * ps + j, row[xcol]);
     }
   }
 }
@@ -350,8 +353,21 @@ extern "C" int missm_patchify(const float* pixels, const int32_t* sample_index, 
     zero_pad_cols_kernel<<<grid_for(rows * (Kpad - K), 256), 256, 0, ST(stream)>>>(
         static_cast<__nv_bfloat16*>(patches), rows, K, Kpad);
   const long warps = static_cast<long>(Bn) * T * C * gh * ps;
-  patchify_kernel<<<grid_for(warps * 32, 256), 256, 0, ST(stream)>>>(
+  patchify_kernel<__nv_bfloat16><<<grid_for(warps * 32, 256), 256, 0, ST(stream)>>>(
       pixels, sample_index, static_cast<__nv_bfloat16*>(patches), Bn, C, T, H, W, ps, gh, gw, Kpad);
+  MISSM_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+/* fp32 verification mode: patches f32 [rows, K] (K = C * ps * ps, no padding) */
+extern "C" int missm_patchify_f32(const float* pixels, const int32_t* sample_index, float* patches,
+                                  int32_t Bn, int32_t C, int32_t T, int32_t H, int32_t W, int32_t ps, void* stream) {
+  if (Bn == 0) return 0;
+  const int gh = H / ps, gw = W / ps, K = C * ps * ps;
+  MISSM_REQUIRE(T >= 1, "patchify_f32: T=%d", T);
+  const long warps = static_cast<long>(Bn) * T * C * gh * ps;
+  patchify_kernel<float><<<grid_for(warps * 32, 256), 256, 0, ST(stream)>>>(pixels, sample_index, patches, Bn, C, T, H,
+                                                                            W, ps, gh, gw, K);
   MISSM_CHECK_CUDA(cudaGetLastError());
   return 0;
 }

@@ -363,3 +363,93 @@ def gather_rows(src, idx, n_rows):
     LAUNCHES[0] += 1
     check(lib().missm_gather_rows(_p(src), _p(idx), _p(dst), n_rows, row_bytes, stream_ptr()), "gather_rows")
     return dst
+
+
+# ------------------------------------------------------------------- fp32 verification mode
+# (MISSM_PRECISION=fp32; csrc/fp32_mode.cu)  Not a performance path: every GEMM expands both fp32 operands into
+# six bf16 pieces along the contraction dimension and runs ONE tcgen05 bf16 GEMM over K' = 6 K.
+def expand6(x, which, stack_rows, cols_pad=None):
+    """fp32 [R, C] (row-major, possibly a strided view) -> bf16 [R, 6 * cols_pad] (stack_rows=False) or
+    [6 * R, C] (stack_rows=True); which = 0: A-operand piece order, 1: B-operand piece order."""
+    assert x.dtype == F32 and x.is_cuda and x.dim() == 2 and x.stride(1) == 1
+    R, C = x.shape
+    cp = C if cols_pad is None else cols_pad
+    out = torch.empty((6 * R, C) if stack_rows else (R, 6 * cp), device=x.device, dtype=BF16)
+    LAUNCHES[0] += 1
+    check(lib().missm_expand6_bf16(_p(x), _ld(x), R, C, _p(out), _ld(out), cp, which, int(stack_rows), stream_ptr()),
+          "expand6_bf16")
+    return out
+
+
+def gemm_f32(a, b, *, a_mn=False, b_mn=False, out=None, bias=None, epilogue=EPI_LINEAR, aux_in=None,
+             scale_cols=0, col_scale=1.0, patch_P=0, out_rows=None):
+    """fp32-grade C = epilogue(A B^T) with fp32 operands and an fp32 result (see module comment above).
+    Layout flags as `gemm`.  Only the LINEAR / RESID / PATCH epilogues (fp32 outputs) are meaningful here."""
+    assert a.dtype == F32 and b.dtype == F32
+    K = a.shape[0] if a_mn else a.shape[1]
+    if not a_mn and not b_mn:
+        kp = (K + 7) // 8 * 8          # both K-major: pad every piece alike (TMA needs 16-byte row pitches)
+    else:
+        assert a_mn and b_mn or K % 8 == 0, "mixed operand layouts need K % 8 == 0"
+        kp = K
+    ea = expand6(a, 0, a_mn, None if a_mn else kp)
+    eb = expand6(b, 1, b_mn, None if b_mn else kp)
+    return gemm(ea, eb, a_mn=a_mn, b_mn=b_mn, out=out, out_dtype=F32, bias=bias, epilogue=epilogue, aux_in=aux_in,
+                scale_cols=scale_cols, col_scale=col_scale, patch_P=patch_P, out_rows=out_rows)
+
+
+def gelu_f32_fwd(u):
+    assert u.dtype == F32 and u.is_contiguous()
+    a = torch.empty_like(u)
+    LAUNCHES[0] += 1
+    check(lib().missm_gelu_f32_fwd(_p(u), _p(a), u.numel(), stream_ptr()), "gelu_f32_fwd")
+    return a
+
+
+def gelu_f32_bwd(d_a, u):
+    assert d_a.dtype == F32 and u.dtype == F32 and d_a.is_contiguous() and u.is_contiguous()
+    d_u = torch.empty_like(u)
+    LAUNCHES[0] += 1
+    check(lib().missm_gelu_f32_bwd(_p(d_a), _p(u), _p(d_u), u.numel(), stream_ptr()), "gelu_f32_bwd")
+    return d_u
+
+
+def attention_f32_fwd(qkv, lay, H, *, causal=False, key_mask=None, mask_rows=None, mask_div=1):
+    """qkv f32 [rows, 3D] (q pre-scaled) -> (out f32 [rows, D], lse f32 [n_seq, H, N])."""
+    assert qkv.dtype == F32 and qkv.is_cuda
+    D = qkv.shape[1] // 3
+    out = torch.empty((qkv.shape[0], D), device=qkv.device, dtype=F32)
+    lse = torch.empty((lay.n_seq, H, lay.N), device=qkv.device, dtype=F32)
+    a = _attn_args(qkv, out, lse, lay, H, causal, key_mask, mask_rows, mask_div)
+    LAUNCHES[0] += 1
+    check(lib().missm_attention_f32_fwd(ctypes.byref(a), stream_ptr()), "attention_f32_fwd")
+    return out, lse
+
+
+def attention_f32_bwd(qkv, out, lse, d_out, lay, H, q_scale, *, causal=False, key_mask=None, mask_rows=None,
+                      mask_div=1):
+    """-> dqkv f32 [rows, 3D]; the q block is the gradient w.r.t. the UN-scaled projection."""
+    assert d_out.dtype == F32 and d_out.shape == out.shape and _ld(d_out) == _ld(out)
+    dqkv = torch.empty_like(qkv)
+    delta = torch.empty_like(lse)
+    a = _attn_args(qkv, out, lse, lay, H, causal, key_mask, mask_rows, mask_div)
+    a.d_out, a.delta, a.dqkv, a.q_scale = d_out.data_ptr(), delta.data_ptr(), dqkv.data_ptr(), q_scale
+    LAUNCHES[0] += 2
+    check(lib().missm_attention_f32_bwd(ctypes.byref(a), stream_ptr()), "attention_f32_bwd")
+    return dqkv
+
+
+def patchify_f32(pixels, ps, T=1, sample_index=None, n_samples=None):
+    """pixels f32 -> f32 [Bn * T * gh * gw, C * ps * ps] patches of the present samples."""
+    assert pixels.dtype == F32 and pixels.is_contiguous()
+    C, H, W = pixels.shape[1], pixels.shape[-2], pixels.shape[-1]
+    Bn = n_samples if n_samples is not None else pixels.shape[0]
+    out = torch.empty((Bn * T * (H // ps) * (W // ps), C * ps * ps), device=pixels.device, dtype=F32)
+    LAUNCHES[0] += 1
+    check(lib().missm_patchify_f32(_p(pixels), _p(sample_index), _p(out), Bn, C, T, H, W, ps, stream_ptr()), "patchify_f32")
+    return out
+
+
+def colsum_f32(x):
+    """f32 [M, N] contiguous -> f32 [N] column sums."""
+    return colsum_grouped(x, 1, 1)[0]

@@ -64,7 +64,7 @@ def test_ctypes_table_matches_header(built):
 def test_library_loads_and_reports_version(built):
     from missm_b200 import _lib
     L = _lib.lib()
-    assert L.missm_version() == 3
+    assert L.missm_version() == 4
     assert isinstance(L.missm_last_error(), bytes)
 
 
