@@ -230,7 +230,7 @@ int missm_fusion_sum_bwd(const missm_fusion_sum_args* args, const float* d_out, 
  * fp32 VERIFICATION mode (host side: MISSM_PRECISION=fp32; csrc/fp32_mode.cu).  Same path, fp32-grade
  * arithmetic, to check embeddings / loss against the reference's fp32 PyTorch path at <= 1e-5.
  * An fp32 GEMM is ONE launch of missm_gemm_bf16 over 3-way bf16 splits of both operands laid out along the
- * contraction dimension (K' = 6 K; pieces x1,x1,x2,x1,x3,x2 against w1,w2,w1,w3,w1,w2): missm_expand6_bf16
+ * contraction dimension (K' = 6 K; pieces x2,x3,x1,x2,x1,x1 against w2,w1,w3,w1,w2,w1, small products first): missm_expand6_bf16
  * builds such an operand from an fp32 matrix [rows, cols] (which = 0: A pattern, 1: B pattern;
  * stack_rows = 0: dst [rows, 6 * cols_pad] for K-major operands, zero padded; 1: dst [6 * rows, cols] for MN-major).
  * missm_attention_f32_*: the CLIPAttention chain in fp32 on the CUDA cores, same layout contract as
@@ -239,7 +239,8 @@ int missm_fusion_sum_bwd(const missm_fusion_sum_args* args, const float* d_out, 
 int missm_expand6_bf16(const float* src, int64_t ld_src, int32_t rows, int32_t cols, void* dst, int64_t ld_dst,
                        int32_t cols_pad, int32_t which, int32_t stack_rows, void* stream);
 int missm_patchify_f32(const float* pixels, const int32_t* sample_index, float* patches, int32_t Bn, int32_t C,
-                       int32_t T, int32_t H, int32_t W, int32_t ps, void* stream);   /* patches f32 [rows, C*ps*ps] */
+                       int32_t T, int32_t H, int32_t W, int32_t ps, int32_t Kpad,
+                       void* stream);   /* patches f32 [rows, Kpad], pre-zeroed by the caller */
 int missm_gelu_f32_fwd(const float* u, float* a, int64_t n, void* stream);
 int missm_gelu_f32_bwd(const float* d_a, const float* u, float* d_u, int64_t n, void* stream);
 int missm_attention_f32_fwd(const missm_attn_args* args, void* stream);

@@ -359,15 +359,17 @@ extern "C" int missm_patchify(const float* pixels, const int32_t* sample_index, 
   return 0;
 }
 
-/* fp32 verification mode: patches f32 [rows, K] (K = C * ps * ps, no padding) */
+/* fp32 verification mode: patches f32 [rows, Kpad]; columns K = C * ps * ps .. Kpad-1 are NOT written
+   (the caller zero-fills the buffer) */
 extern "C" int missm_patchify_f32(const float* pixels, const int32_t* sample_index, float* patches,
-                                  int32_t Bn, int32_t C, int32_t T, int32_t H, int32_t W, int32_t ps, void* stream) {
+                                  int32_t Bn, int32_t C, int32_t T, int32_t H, int32_t W, int32_t ps, int32_t Kpad,
+                                  void* stream) {
   if (Bn == 0) return 0;
   const int gh = H / ps, gw = W / ps, K = C * ps * ps;
-  MISSM_REQUIRE(T >= 1, "patchify_f32: T=%d", T);
+  MISSM_REQUIRE(T >= 1 && Kpad >= K, "patchify_f32: T=%d Kpad=%d K=%d", T, Kpad, K);
   const long warps = static_cast<long>(Bn) * T * C * gh * ps;
   patchify_kernel<float><<<grid_for(warps * 32, 256), 256, 0, ST(stream)>>>(pixels, sample_index, patches, Bn, C, T, H,
-                                                                            W, ps, gh, gw, K);
+                                                                            W, ps, gh, gw, Kpad);
   MISSM_CHECK_CUDA(cudaGetLastError());
   return 0;
 }

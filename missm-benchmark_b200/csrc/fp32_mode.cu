@@ -4,9 +4,10 @@
 //
 // tcgen05 has no fp32 MMA, so an fp32 GEMM runs on the SAME bf16 tcgen05 kernel through a 3-way split
 //   x = x1 + x2 + x3,  w = w1 + w2 + w3      (bf16 pieces: 3 x 8 mantissa bits = fp32's 24)
-//   x.w ~= x1w1 + x1w2 + x2w1 + x1w3 + x3w1 + x2w2      (dropped terms <= 2^-32 |x||w|)
-// laid out along the contraction dimension: A' = [x1|x1|x2|x1|x3|x2], B' = [w1|w2|w1|w3|w1|w2] (K' = 6 K), so ONE
-// launch accumulates all six products in the fp32 TMEM accumulator (missm_expand6_bf16 builds A' / B').
+//   x.w ~= x2w2 + x3w1 + x1w3 + x2w1 + x1w2 + x1w1      (dropped terms x2w3, x3w2, x3w3 <= 2^-24 |x||w|)
+// laid out along the contraction dimension, SMALLEST products first so that they meet a small accumulator:
+// A' = [x2|x3|x1|x2|x1|x1], B' = [w2|w1|w3|w1|w2|w1] (K' = 6 K), so ONE launch accumulates all six products in
+// the fp32 TMEM accumulator (missm_expand6_bf16 builds A' / B').
 // Attention, QuickGELU and the split run on the CUDA cores in fp32 with expf.
 #include "../../include/missm_b200.h"
 #include "missm_common.cuh"
@@ -15,7 +16,7 @@ namespace missm {
 
 // ---------------------------------------------------------------------------------------
 // 3-way bf16 split of an fp32 matrix, six pieces in the order the GEMM operand needs
-//   which = 0 (A operand): 1,1,2,1,3,2     which = 1 (B operand): 1,2,1,3,1,2
+//   which = 0 (A operand): 2,3,1,2,1,1     which = 1 (B operand): 2,1,3,1,2,1
 //   stack_rows = 0: dst[r, p * cols_pad + c]  (K-major operand, K = cols; columns cols..cols_pad-1 are zero)
 //   stack_rows = 1: dst[p * rows + r, c]      (MN-major operand, K = rows)
 // ---------------------------------------------------------------------------------------
@@ -31,7 +32,7 @@ __global__ void expand6_kernel(const float* __restrict__ src, long ld_src, int r
     const float r1 = x - __bfloat162float(pc[0]);
     pc[1] = __float2bfloat16_rn(r1);
     pc[2] = __float2bfloat16_rn(r1 - __bfloat162float(pc[1]));
-    const int pat_a[6] = {0, 0, 1, 0, 2, 1}, pat_b[6] = {0, 1, 0, 2, 0, 1};
+    const int pat_a[6] = {1, 2, 0, 1, 0, 0}, pat_b[6] = {1, 0, 2, 0, 1, 0};
 #pragma unroll
     for (int p = 0; p < 6; ++p) {
       const __nv_bfloat16 v = pc[which == 0 ? pat_a[p] : pat_b[p]];
@@ -223,6 +224,7 @@ static int fill_f32_params(const missm_attn_args* a, AttnF32Params& p) {
   MISSM_REQUIRE(a->head_dim == 64 && a->D == a->H * 64, "attention_f32: head_dim must be 64 (D=%d H=%d)", a->D, a->H);
   MISSM_REQUIRE(a->N >= 1 && a->N <= F32_MAXN, "attention_f32: N=%d out of range (<= %d)", a->N, F32_MAXN);
   MISSM_REQUIRE(a->ld_qkv % 4 == 0 && a->ld_o % 4 == 0, "attention_f32: leading dimensions must be multiples of 4");
+  MISSM_REQUIRE(a->n_seq <= 65535 && a->H <= 65535, "attention_f32: n_seq=%d exceeds the grid (verification sizes only)", a->n_seq);
   p.qkv = static_cast<const float*>(a->qkv), p.ld_qkv = a->ld_qkv;
   p.D = a->D, p.H = a->H, p.N = a->N, p.n_seq = a->n_seq, p.s_in = a->s_in;
   p.seq_outer = a->seq_outer, p.seq_inner = a->seq_inner, p.tok_stride = a->tok_stride;

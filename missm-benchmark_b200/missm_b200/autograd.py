@@ -40,6 +40,27 @@ def _bf16_of(grad_f32):
     return b, ops.colsum(b)
 
 
+# ------------------------------------------------------------------------------------------
+# precision mode: 'bf16' (the product path) or 'fp32' (verification mode, autograd_f32.py)
+# ------------------------------------------------------------------------------------------
+_PRECISION = [os.environ.get("MISSM_PRECISION", "bf16").lower()]
+
+
+def set_precision(mode):
+    """'bf16': tcgen05 bf16 operands / fp32 accumulate (default).  'fp32': the verification mode -- same path,
+    fp32-grade arithmetic (3-way split GEMMs, fp32 attention), for <= 1e-5 parity checks.  Returns the old mode."""
+    if mode not in ("bf16", "fp32"):
+        raise ValueError(f"precision must be 'bf16' or 'fp32', got {mode!r}")
+    old, _PRECISION[0] = _PRECISION[0], mode
+    return old
+
+
+def get_precision():
+    if _PRECISION[0] not in ("bf16", "fp32"):
+        raise ValueError(f"MISSM_PRECISION must be 'bf16' or 'fp32', got {_PRECISION[0]!r}")
+    return _PRECISION[0]
+
+
 def reset_side_channel():
     _GRAD_BF16.clear()
 
@@ -318,3 +339,29 @@ class BackwardSmsFn(torch.autograd.Function):
     def backward(ctx, g):
         ops.set_persistent_sms(ctx.n_sms)
         return g, None
+
+
+# ------------------------------------------------------------------------------------------
+# block entry points used by the module trees: dispatch on the precision mode
+# ------------------------------------------------------------------------------------------
+def _pick(bf16_fn, f32_name):
+    if get_precision() == "fp32":
+        from . import autograd_f32
+        return getattr(autograd_f32, f32_name)
+    return bf16_fn
+
+
+def attn_block(*args):
+    return _pick(AttnBlockFn, "AttnBlockF32Fn").apply(*args)
+
+
+def mlp_block(*args):
+    return _pick(MlpBlockFn, "MlpBlockF32Fn").apply(*args)
+
+
+def vision_embed(*args):
+    return _pick(VisionEmbedFn, "VisionEmbedF32Fn").apply(*args)
+
+
+def pool_proj(*args):
+    return _pick(PoolProjFn, "PoolProjF32Fn").apply(*args)

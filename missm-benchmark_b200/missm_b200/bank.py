@@ -40,6 +40,16 @@ def _ddp_backward_sms():
     return int(os.environ.get("MISSM_DDP_SMS", "0"))
 
 
+def _require_cuda_index(mi, mdev):
+    """missing_index on the host is uploaded when the model lives on a CUDA device; there is no CPU path."""
+    if not mi.is_cuda:
+        if mdev.type != 'cuda':
+            raise RuntimeError("missm_b200: missing_index is on the CPU; the B200 path has no CPU fallback "
+                               "(move the model and its inputs to a CUDA device)")
+        mi = mi.to(mdev, non_blocking=True)
+    return mi
+
+
 class _ZeroTower(torch.autograd.Function):
     """A tower that saw zero present samples on this rank still has to hand DDP a gradient for
     every parameter (find_unused_parameters=False, train_ddp.py:189): emit zero embeddings whose
@@ -135,11 +145,7 @@ class LanguageBind(nn.Module):
         mdev = self._param_device()
         if missing_index is not None and self.compaction and len(keys) > 0:
             mi = missing_index.reshape(-1).to(torch.int64).contiguous()
-            if not mi.is_cuda:
-                if mdev.type != 'cuda':
-                    raise RuntimeError("missm_b200: missing_index is on the CPU; the B200 path has no CPU fallback "
-                                       "(move the model and its inputs to a CUDA device)")
-                mi = mi.to(mdev, non_blocking=True)
+            mi = _require_cuda_index(mi, mdev)
             codes = [MISSING_TYPE_INDEX.get(k, -1) for k in keys]
             idx, slot, counts = ops.compact_mask(mi, codes)
             counts = counts.tolist()          # the one host sync of the step: sizes of the towers' batches

@@ -382,7 +382,7 @@ def expand6(x, which, stack_rows, cols_pad=None):
 
 
 def gemm_f32(a, b, *, a_mn=False, b_mn=False, out=None, bias=None, epilogue=EPI_LINEAR, aux_in=None,
-             scale_cols=0, col_scale=1.0, patch_P=0, out_rows=None):
+             scale_cols=0, col_scale=1.0, patch_P=0, out_rows=None, split_k=0):
     """fp32-grade C = epilogue(A B^T) with fp32 operands and an fp32 result (see module comment above).
     Layout flags as `gemm`.  Only the LINEAR / RESID / PATCH epilogues (fp32 outputs) are meaningful here."""
     assert a.dtype == F32 and b.dtype == F32
@@ -395,7 +395,7 @@ def gemm_f32(a, b, *, a_mn=False, b_mn=False, out=None, bias=None, epilogue=EPI_
     ea = expand6(a, 0, a_mn, None if a_mn else kp)
     eb = expand6(b, 1, b_mn, None if b_mn else kp)
     return gemm(ea, eb, a_mn=a_mn, b_mn=b_mn, out=out, out_dtype=F32, bias=bias, epilogue=epilogue, aux_in=aux_in,
-                scale_cols=scale_cols, col_scale=col_scale, patch_P=patch_P, out_rows=out_rows)
+                scale_cols=scale_cols, col_scale=col_scale, patch_P=patch_P, out_rows=out_rows, split_k=split_k)
 
 
 def gelu_f32_fwd(u):
@@ -439,14 +439,15 @@ def attention_f32_bwd(qkv, out, lse, d_out, lay, H, q_scale, *, causal=False, ke
     return dqkv
 
 
-def patchify_f32(pixels, ps, T=1, sample_index=None, n_samples=None):
-    """pixels f32 -> f32 [Bn * T * gh * gw, C * ps * ps] patches of the present samples."""
+def patchify_f32(pixels, ps, Kpad, T=1, sample_index=None, n_samples=None):
+    """pixels f32 -> f32 [Bn * T * gh * gw, Kpad] patches of the present samples (zero padded columns)."""
     assert pixels.dtype == F32 and pixels.is_contiguous()
     C, H, W = pixels.shape[1], pixels.shape[-2], pixels.shape[-1]
     Bn = n_samples if n_samples is not None else pixels.shape[0]
-    out = torch.empty((Bn * T * (H // ps) * (W // ps), C * ps * ps), device=pixels.device, dtype=F32)
+    out = torch.zeros((Bn * T * (H // ps) * (W // ps), Kpad), device=pixels.device, dtype=F32)
     LAUNCHES[0] += 1
-    check(lib().missm_patchify_f32(_p(pixels), _p(sample_index), _p(out), Bn, C, T, H, W, ps, stream_ptr()), "patchify_f32")
+    check(lib().missm_patchify_f32(_p(pixels), _p(sample_index), _p(out), Bn, C, T, H, W, ps, Kpad, stream_ptr()),
+          "patchify_f32")
     return out
 
 

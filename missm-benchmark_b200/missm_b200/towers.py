@@ -96,17 +96,17 @@ class CLIPEncoderLayer(nn.Module):
         """x: fp32 [M, D] residual stream, rows ordered (image, token)."""
         if self.add_time_attn:
             temb = self.temporal_embedding if self.t != 1 else None
-            x = ag.AttnBlockFn.apply(x, temporal_meta, self._cache["ta"],
+            x = ag.attn_block(x, temporal_meta, self._cache["ta"],
                                      *self._attn_params(self.temporal_layer_norm1, self.temporal_attn), temb)
             if self.has_temporal_mlp:
                 m = self.temporal_mlp
-                x = ag.MlpBlockFn.apply(x, self.eps, self._cache["tmlp"], self.temporal_layer_norm2.weight,
+                x = ag.mlp_block(x, self.eps, self._cache["tmlp"], self.temporal_layer_norm2.weight,
                                         self.temporal_layer_norm2.bias, m.fc1.weight, m.fc1.bias,
                                         m.fc2.weight, m.fc2.bias)
-        x = ag.AttnBlockFn.apply(x, spatial_meta, self._cache["sa"],
+        x = ag.attn_block(x, spatial_meta, self._cache["sa"],
                                  *self._attn_params(self.layer_norm1, self.self_attn), None)
         m = self.mlp
-        x = ag.MlpBlockFn.apply(x, self.eps, self._cache["mlp"], self.layer_norm2.weight, self.layer_norm2.bias,
+        x = ag.mlp_block(x, self.eps, self._cache["mlp"], self.layer_norm2.weight, self.layer_norm2.bias,
                                 m.fc1.weight, m.fc1.bias, m.fc2.weight, m.fc2.bias)
         return x
 
@@ -213,7 +213,7 @@ class CLIPVisionTransformer(nn.Module):
         P, D = emb.num_patches, cfg.hidden_size
         N = P + 1
         geom = (cfg.patch_size, Tp, emb.grid[0], emb.grid[1], cfg.layer_norm_eps)
-        x = ag.VisionEmbedFn.apply(px, present_idx, n_samp, geom, self._cache["embed"], emb.class_embedding,
+        x = ag.vision_embed(px, present_idx, n_samp, geom, self._cache["embed"], emb.class_embedding,
                                    emb.patch_embedding.weight, emb.position_embedding.weight,
                                    self.pre_layrnorm.weight, self.pre_layrnorm.bias)
         n_img = n_samp * Tp
@@ -239,7 +239,7 @@ def _pool(owner, x, rows, n_present, T, ln, proj, scale, eps):
     if proj is None:
         # standalone tower call: pooled = LayerNorm(rows) (mean over frames); identity "projection"
         raise NotImplementedError("call the tower through LanguageBind (projection is fused into the tail)")
-    return ag.PoolProjFn.apply(x, rows, n_present, T, eps, scale, owner._cache["pool"], ln.weight, ln.bias,
+    return ag.pool_proj(x, rows, n_present, T, eps, scale, owner._cache["pool"], ln.weight, ln.bias,
                                proj.weight)
 
 

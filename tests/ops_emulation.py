@@ -1,0 +1,310 @@
+"""TEST INFRASTRUCTURE ONLY: torch-CPU stand-ins for the C-ABI entry points (include/missm_b200.h), written
+from the ABI contracts, so that the HOST logic above the ABI (autograd wiring of the fp32 verification mode,
+operand layouts of the 3-way split GEMM, mask compaction plumbing) can be exercised by `-m "not gpu"` tests in a
+container without a GPU.  Nothing under missm-benchmark_b200/ imports this file; the product has no CPU path
+(tests/test_host_logic.py::test_product_has_no_cpu_fallback).  The CUDA kernels themselves are checked by the
+`-m gpu` tests.
+"""
+import contextlib
+
+import torch
+
+BF16, F32 = torch.bfloat16, torch.float32
+EPI_LINEAR, EPI_GELU, EPI_RESID, EPI_DGELU, EPI_PATCH = range(5)
+
+
+def _gelu(x):
+    return x * torch.sigmoid(1.702 * x)
+
+
+def _gelu_grad(x):
+    s = torch.sigmoid(1.702 * x)
+    return s + 1.702 * x * s * (1 - s)
+
+
+# ------------------------------------------------------------------ missm_gemm_bf16 (bf16 operands, fp32 accumulate)
+def gemm(a, b, *, a_mn=False, b_mn=False, out=None, out_dtype=BF16, bias=None, epilogue=EPI_LINEAR, aux_in=None,
+         aux_out=None, scale_cols=0, col_scale=1.0, patch_P=0, out_rows=None, split_k=0, force_bn=0,
+         colsum_out=None):
+    assert a.dtype == BF16 and b.dtype == BF16
+    A = (a.t() if a_mn else a).double()
+    Bm = (b.t() if b_mn else b).double()
+    assert A.shape[1] == Bm.shape[1], (A.shape, Bm.shape)
+    M, N = A.shape[0], Bm.shape[0]
+    assert N % 8 == 0 and (a.stride(0) * 2) % 16 == 0 and (b.stride(0) * 2) % 16 == 0, "TMA pitch / N rules"
+    v = (A @ Bm.t()).float()
+    if bias is not None:
+        v = v + bias
+    if epilogue == EPI_LINEAR:
+        if scale_cols:
+            v[:, :scale_cols] *= col_scale
+    elif epilogue == EPI_GELU:
+        aux_out.copy_(v.to(aux_out.dtype))
+        v = _gelu(v)
+    elif epilogue == EPI_RESID:
+        v = v + aux_in.float()
+    elif epilogue == EPI_DGELU:
+        v = v * _gelu_grad(aux_in.float())
+    elif epilogue == EPI_PATCH:
+        r = torch.arange(M)
+        v = v + aux_in[1 + r % patch_P]
+    if out is None:
+        out = torch.empty((out_rows if out_rows is not None else M, N), dtype=out_dtype)
+    if epilogue == EPI_PATCH:
+        r = torch.arange(M)
+        out[(r // patch_P) * (patch_P + 1) + 1 + r % patch_P] = v.to(out.dtype)
+    else:
+        out[:M] = v.to(out.dtype)
+    return out
+
+
+# ------------------------------------------------------------------ missm_expand6_bf16 (csrc/fp32_mode.cu)
+def expand6(x, which, stack_rows, cols_pad=None):
+    assert x.dtype == F32 and x.dim() == 2 and x.stride(1) == 1
+    R, C = x.shape
+    cp = C if cols_pad is None else cols_pad
+    p1 = x.to(BF16)
+    r1 = x - p1.float()
+    p2 = r1.to(BF16)
+    p3 = (r1 - p2.float()).to(BF16)
+    pc = [p1, p2, p3]
+    order = ([1, 2, 0, 1, 0, 0], [1, 0, 2, 0, 1, 0])[which]
+    if stack_rows:
+        assert cp == C
+        return torch.cat([pc[i] for i in order], dim=0)
+    out = torch.zeros((R, 6 * cp), dtype=BF16)
+    for p, i in enumerate(order):
+        out[:, p * cp:p * cp + C] = pc[i]
+    return out
+
+
+# ------------------------------------------------------------------ attention (fp32 verification kernels)
+def _seq_rows(lay):
+    s = torch.arange(lay.n_seq)
+    t = torch.arange(lay.N)
+    return ((s // lay.s_in) * lay.seq_outer + (s % lay.s_in) * lay.seq_inner)[:, None] + t[None, :] * lay.tok_stride
+
+
+def _attn_core(qkv, lay, H, causal, key_mask, mask_rows, mask_div):
+    D = qkv.shape[1] // 3
+    rows = _seq_rows(lay)                                      # [S, N]
+    x = qkv[rows.reshape(-1)].reshape(lay.n_seq, lay.N, 3, H, D // H)
+    q, k, v = (x[:, :, i].permute(0, 2, 1, 3) for i in range(3))          # [S, H, N, hd]
+    sc = q @ k.transpose(-1, -2)
+    neg = torch.zeros((lay.n_seq, 1, lay.N, lay.N))
+    if causal:
+        neg = neg + torch.full((lay.N, lay.N), float('-inf')).triu(1)
+    if key_mask is not None:
+        r = torch.arange(lay.n_seq) // mask_div
+        if mask_rows is not None:
+            r = mask_rows[r].long()
+        km = key_mask[r]                                        # [S, N]
+        neg = neg + torch.where(km == 0, float('-inf'), 0.0)[:, None, None, :]
+    sc = sc + neg
+    lse = torch.logsumexp(sc, dim=-1)                           # [S, H, N]
+    o = torch.softmax(sc, dim=-1) @ v                           # [S, H, N, hd]
+    out = torch.zeros((qkv.shape[0], D))
+    out[rows.reshape(-1)] = o.permute(0, 2, 1, 3).reshape(-1, D)
+    return out, lse
+
+
+def attention_f32_fwd(qkv, lay, H, *, causal=False, key_mask=None, mask_rows=None, mask_div=1):
+    assert qkv.dtype == F32
+    with torch.no_grad():
+        return _attn_core(qkv, lay, H, causal, key_mask, mask_rows, mask_div)
+
+
+def attention_f32_bwd(qkv, out, lse, d_out, lay, H, q_scale, *, causal=False, key_mask=None, mask_rows=None,
+                      mask_div=1):
+    D = qkv.shape[1] // 3
+    with torch.enable_grad():
+        x = qkv.detach().clone().requires_grad_(True)
+        o, _ = _attn_core(x, lay, H, causal, key_mask, mask_rows, mask_div)
+        (g,) = torch.autograd.grad(o, x, d_out)
+    g = g.clone()
+    g[:, :D] *= q_scale
+    return g
+
+
+# ------------------------------------------------------------------ layernorm
+def layernorm_fwd(x, gamma, beta, eps, *, out_dtype=BF16, row_index=None, n_rows=None, add_rows=None, add_period=0,
+                  add_div=0, x_out=None, want_stats=True):
+    xs = x
+    if row_index is not None:
+        xs = x[row_index[:n_rows].long() if n_rows is not None else row_index.long()]
+    elif n_rows is not None:
+        xs = x[:n_rows]
+    if add_rows is not None:
+        r = torch.arange(xs.shape[0])
+        xs = xs + add_rows[(r // add_div) % add_period]
+        (x_out if x_out is not None else x).copy_(xs)
+    mean = xs.mean(-1)
+    var = ((xs - mean[:, None]) ** 2).mean(-1)
+    rstd = (var + eps).rsqrt()
+    y = ((xs - mean[:, None]) * rstd[:, None] * gamma.detach() + beta.detach()).to(out_dtype)
+    return y, mean, rstd
+
+
+def layernorm_bwd(dy, x, mean, rstd, gamma, *, dres=None, row_index=None, dx=None, want_bf16=False, dx_bf16=None):
+    dyf = dy.float()
+    xs = x if row_index is None else x[row_index[:dy.shape[0]].long()]
+    xhat = (xs - mean[:, None]) * rstd[:, None]
+    g = dyf * gamma.detach()
+    d = rstd[:, None] * (g - g.mean(-1, keepdim=True) - xhat * (g * xhat).mean(-1, keepdim=True))
+    if dres is not None:
+        d = d + dres
+    if row_index is None:
+        dx = d
+    else:
+        dx[row_index[:dy.shape[0]].long()] = d
+    return dx, None, (dyf * xhat).sum(0), dyf.sum(0), d.sum(0)
+
+
+# ------------------------------------------------------------------ small kernels
+def gelu_f32_fwd(u):
+    return _gelu(u)
+
+
+def gelu_f32_bwd(d_a, u):
+    return d_a * _gelu_grad(u)
+
+
+def colsum_grouped(x, period, div):
+    r = torch.arange(x.shape[0])
+    g = (r // div) % period
+    out = torch.zeros((period, x.shape[1]))
+    out.index_add_(0, g, x)
+    return out
+
+
+def copy_f32(src, dst):
+    dst.copy_(src.reshape(dst.shape))
+    return dst
+
+
+def _sample_rows(t, sample_index, n):
+    return t[sample_index[:n].long()] if sample_index is not None else t[:n]
+
+
+def patchify_f32(pixels, ps, Kpad, T=1, sample_index=None, n_samples=None):
+    Bn = n_samples if n_samples is not None else pixels.shape[0]
+    px = _sample_rows(pixels, sample_index, Bn)
+    if T == 1:
+        px = px.unsqueeze(2)                                    # b c 1 h w
+    b, c, t, h, w = px.shape
+    gh, gw = h // ps, w // ps
+    p = px[:, :, :, :gh * ps, :gw * ps].reshape(b, c, t, gh, ps, gw, ps).permute(0, 2, 3, 5, 1, 4, 6)
+    p = p.reshape(b * t * gh * gw, c * ps * ps)
+    out = torch.zeros((p.shape[0], Kpad))
+    out[:, :p.shape[1]] = p
+    return out
+
+
+def cls_rows(cls, pos, tok, Bn, ntok):
+    tok[torch.arange(Bn) * ntok] = cls + pos[0]
+
+
+def embed_bwd(dtok, Bn, ntok):
+    return dtok.reshape(Bn, ntok, -1).sum(0), None
+
+
+def frame_mean(x, Bn, T, out_dtype=BF16):
+    return x.reshape(Bn, T, -1).mean(1).to(out_dtype)
+
+
+def frame_mean_bwd(dout, Bn, T):
+    return (dout[:, None, :] / T).expand(Bn, T, dout.shape[1]).reshape(Bn * T, -1).contiguous()
+
+
+def l2norm_scale_fwd(x, scale):
+    inv = 1.0 / x.norm(dim=-1)
+    return x * inv[:, None] * scale, inv
+
+
+def l2norm_scale_bwd(dy, x, inv, scale, out_dtype=BF16):
+    yh = x * inv[:, None]
+    return (scale * inv[:, None] * (dy - yh * (dy * yh).sum(-1, keepdim=True))).to(out_dtype)
+
+
+def text_embed_fwd(ids, tok_emb, pos_emb, sample_index=None, n_samples=None):
+    Bn = n_samples if n_samples is not None else ids.shape[0]
+    i = _sample_rows(ids, sample_index, Bn)
+    return (tok_emb[i] + pos_emb[None, :ids.shape[1]]).reshape(Bn * ids.shape[1], -1)
+
+
+def text_embed_bwd(ids, dx, vocab, sample_index=None, n_samples=None):
+    Bn = n_samples if n_samples is not None else ids.shape[0]
+    L, D = ids.shape[1], dx.shape[1]
+    i = _sample_rows(ids, sample_index, Bn)
+    dtok = torch.zeros((vocab, D))
+    dtok.index_add_(0, i.reshape(-1), dx)
+    return dtok, dx.reshape(Bn, L, D).sum(0)
+
+
+def argmax_rows(ids, sample_index=None, n_samples=None):
+    Bn = n_samples if n_samples is not None else ids.shape[0]
+    i = _sample_rows(ids, sample_index, Bn)
+    return (torch.arange(Bn) * ids.shape[1] + i.to(torch.int32).argmax(-1)).to(torch.int32)
+
+
+def compact_mask(missing_index, codes):
+    B, T = missing_index.numel(), len(codes)
+    idx = torch.zeros((T, B), dtype=torch.int32)
+    slot = torch.full((T, B), -1, dtype=torch.int32)
+    counts = torch.zeros((T,), dtype=torch.int32)
+    for t, c in enumerate(codes):
+        present = torch.nonzero(missing_index != c).reshape(-1).to(torch.int32)
+        n = present.numel()
+        idx[t, :n] = present
+        slot[t, present.long()] = torch.arange(n, dtype=torch.int32)
+        counts[t] = n
+    return idx, slot, counts
+
+
+def scatter_rows_zero(src, slot_of, B):
+    dst = torch.zeros((B, src.shape[1]))
+    ok = slot_of[:B] >= 0
+    dst[ok] = src[slot_of[:B][ok].long()]
+    return dst
+
+
+def gather_rows(src, idx, n_rows):
+    return src[idx[:n_rows].long()].clone()
+
+
+def masked_sum_norm(embs, weights, biases, codes, missing_index, gamma, beta, eps):
+    """modal_sum.forward, src/model/baseline.py:52-61 (what csrc/fusion.cu computes)."""
+    tot = 0
+    for e, w, b, c in zip(embs, weights, biases, codes):
+        y = torch.nn.functional.linear(e.float(), w, b)
+        tot = tot + torch.where((missing_index.reshape(-1) == c)[:, None], torch.zeros_like(y), y)
+    return torch.nn.functional.layer_norm(tot, (tot.shape[1],), gamma, beta, eps)
+
+
+EMULATED_OPS = ["gemm", "expand6", "attention_f32_fwd", "attention_f32_bwd", "layernorm_fwd", "layernorm_bwd",
+                "gelu_f32_fwd", "gelu_f32_bwd", "colsum_grouped", "copy_f32", "patchify_f32", "cls_rows", "embed_bwd",
+                "frame_mean", "frame_mean_bwd", "l2norm_scale_fwd", "l2norm_scale_bwd", "text_embed_fwd",
+                "text_embed_bwd", "argmax_rows", "compact_mask", "scatter_rows_zero", "gather_rows"]
+
+
+@contextlib.contextmanager
+def emulated_fp32_mode():
+    """Patch missm_b200.ops (+ the fused `sum` head and the CUDA-only guards) with the stand-ins above and switch
+    the host side to the fp32 verification mode.  ops.gemm_f32 / colsum_f32 stay the REAL host code."""
+    from missm_b200 import autograd as ag, bank, fusion_ops, ops, towers
+    here = globals()
+    saved = {n: getattr(ops, n) for n in EMULATED_OPS}
+    saved_guard, saved_bank_guard, saved_fusion = towers._require_cuda, bank._require_cuda_index, fusion_ops.masked_sum_norm
+    for n in EMULATED_OPS:
+        setattr(ops, n, here[n])
+    towers._require_cuda = lambda t, what: None
+    bank._require_cuda_index = lambda mi, mdev: mi
+    fusion_ops.masked_sum_norm = masked_sum_norm
+    old = ag.set_precision("fp32")
+    try:
+        yield
+    finally:
+        ag.set_precision(old)
+        for n, f in saved.items():
+            setattr(ops, n, f)
+        towers._require_cuda, bank._require_cuda_index, fusion_ops.masked_sum_norm = saved_guard, saved_bank_guard, saved_fusion

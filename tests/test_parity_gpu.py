@@ -187,6 +187,22 @@ def test_config1_full_size_matches_reference_golden():
         assert rel(emb[m], g[f'emb/{m}']) < TOL, (m, rel(emb[m], g[f'emb/{m}']))
     print('config1 logits', rel(logits, g['logits/sum']))
     assert rel(logits, g['logits/sum']) < TOL_LOGIT
+    # the same full-size forward in the fp32 VERIFICATION mode (3-way split tcgen05 GEMMs, fp32 attention):
+    # north_star's fp32 tolerance, <= 1e-5 relative on the embeddings, through all 24 / 12 layers
+    from missm_b200 import autograd as ag
+    old = ag.set_precision("fp32")
+    try:
+        with torch.no_grad():
+            emb32 = model.encoder(data)
+            logits32 = model(data, mi)
+    finally:
+        ag.set_precision(old)
+    for m in modal_types:
+        print('config1 fp32 mode', m, rel(emb32[m], g[f'emb/{m}']))
+    print('config1 fp32 mode logits', rel(logits32, g['logits/sum']))
+    for m in modal_types:
+        assert rel(emb32[m], g[f'emb/{m}']) < 1e-5, (m, rel(emb32[m], g[f'emb/{m}']))
+    assert rel(logits32, g['logits/sum']) < 1e-4
     # B = 4 training step: loss and gradient norms
     model.train()
     data4 = {k: {kk: vv[:4] for kk, vv in v.items()} for k, v in data.items()}
