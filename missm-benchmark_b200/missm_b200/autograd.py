@@ -149,19 +149,169 @@ class AttnBlockFn(torch.autograd.Function):
         hd = D // meta.H
         d_out = _contig(d_out)
         d_out_b, d_ob = _bf16_of(d_out)
-        d_ow = ops.gemm(d_out_b, attn, a_mn=True, b_mn=True, out_dtype=F32)          # dY^T @ attn
+        # a frozen encoder (peft freezes everything but the adapters, modeling_image.py:793) asks for no weight
+        # gradients: dgrad only
+        wgrads = any(ctx.needs_input_grad[5:13])
+        d_ow = ops.gemm(d_out_b, attn, a_mn=True, b_mn=True, out_dtype=F32) if wgrads else None   # dY^T @ attn
         d_attn = ops.gemm(d_out_b, wo, b_mn=True)                                      # dY @ Wo
         dqkv, d_bqkv = ops.attention_bwd(qkv, attn, lse, d_attn, meta.layout, meta.H, hd ** -0.5, causal=meta.causal,
-                                         key_mask=meta.key_mask, mask_rows=meta.mask_rows, mask_div=meta.mask_div)
-        d_wqkv = ops.gemm(dqkv, h, a_mn=True, b_mn=True, out_dtype=F32)               # [3D, D]
+                                         key_mask=meta.key_mask, mask_rows=meta.mask_rows, mask_div=meta.mask_div,
+                                         want_colsum=wgrads)
+        d_wqkv = ops.gemm(dqkv, h, a_mn=True, b_mn=True, out_dtype=F32) if wgrads else None      # [3D, D]
         d_h = ops.gemm(dqkv, wqkv, b_mn=True)
         dx, dx_b, d_lnw, d_lnb, dx_cs = ops.layernorm_bwd(d_h, x_res, mean, rstd, ln_w, dres=d_out, want_bf16=True)
         _publish_bf16(dx, dx_b, dx_cs)
         d_temb = None
         if ctx.has_temb:
             d_temb = ops.colsum_grouped(dx, meta.add_period, meta.add_div).view(1, meta.add_period, D)
+        if not wgrads:
+            return (dx, None, None, d_lnw, d_lnb) + (None,) * 8 + (d_temb,)
         return (dx, None, None, d_lnw, d_lnb, d_wqkv[:D], d_bqkv[:D], d_wqkv[D:2 * D], d_bqkv[D:2 * D],
                 d_wqkv[2 * D:], d_bqkv[2 * D:], d_ow, d_ob, d_temb)
+
+
+# ------------------------------------------------------------------------------------------
+# The same block with peft LoRA adapters on q / k / v / out_proj (reference: convert_to_lora,
+# modeling_image.py:775-793; peft's Linear: y = W x + b + (alpha / r) B(A(x))).
+#
+# Adapters ride on the tcgen05 GEMMs through the CONTRACTION dimension instead of being merged into W (a bf16
+# copy of W + sBA would round away a delta that is ~2^-8 of W early in training) or run as separate rank-r GEMM
+# chains: with T = X A_cat^T (one skinny GEMM, r_pad = 8 columns per group) stored NEXT to X in one row-major
+# buffer [X | T], the layer is ONE GEMM over K' = K + r_pad against [W | sB]; in the backward [dY | dY sB] against
+# the row-stacked [W ; A_cat] gives dX in ONE GEMM, and dA_cat = (dY sB)^T X, d(sB) = dY^T T are two skinny
+# wgrads.  Every operand is a column view of a wider-pitched buffer; nothing is copied or transposed.
+# The encoder's own weights are frozen by peft, so their wgrads / bias sums are skipped (needs_input_grad).
+# ------------------------------------------------------------------------------------------
+def _pad8(n):
+    return (n + 7) // 8 * 8
+
+
+def lora_packs(cache, base, adapters, scaling):
+    """bf16 operand buffers of one LoRA attention block.  Parameter-space work (a few [D, r] slices per layer, done
+    with torch indexing / casts, re-done only when a parameter changes): the frozen base part is written once,
+    the adapter columns / rows are refreshed in place after an optimizer step."""
+    qw, qb, kw, kb, vw, vb, ow, ob = base
+    qA, qB, kA, kB, vA, vB, oA, oB = adapters
+    D, r = qw.shape[0], qA.shape[0]
+    R3, R1 = _pad8(3 * r), _pad8(r)
+
+    def build_base():
+        dev = qw.device
+        wf_qkv = torch.zeros((3 * D, D + R3), device=dev, dtype=BF16)       # [W | sB]   fwd operand / dT operand
+        wb_qkv = torch.zeros((3 * D + R3, D), device=dev, dtype=BF16)       # [W ; A]    dgrad operand (MN-major)
+        wf_o = torch.zeros((D, D + R1), device=dev, dtype=BF16)
+        wb_o = torch.zeros((D + R1, D), device=dev, dtype=BF16)
+        for i, w in enumerate((qw, kw, vw)):
+            wb_qkv[i * D:(i + 1) * D] = w.detach()
+        wf_qkv[:, :D] = wb_qkv[:3 * D]
+        wb_o[:D] = ow.detach()
+        wf_o[:, :D] = wb_o[:D]
+        bqkv = torch.cat([qb.detach(), kb.detach(), vb.detach()]).float().contiguous()
+        return wf_qkv, wb_qkv, wf_o, wb_o, bqkv
+
+    packs = cached_weight(cache, "lora_base", base, build_base)
+    wf_qkv, wb_qkv, wf_o, wb_o, bqkv = packs
+
+    def fill_adapters():
+        with torch.no_grad():
+            for i, (A, B) in enumerate(((qA, qB), (kA, kB), (vA, vB))):
+                wf_qkv[i * D:(i + 1) * D, D + i * r:D + (i + 1) * r] = B.detach() * scaling
+                wb_qkv[3 * D + i * r:3 * D + (i + 1) * r] = A.detach()
+            wf_o[:, D:D + r] = oB.detach() * scaling
+            wb_o[D:D + r] = oA.detach()
+        return True
+
+    ver = tuple((p._version, p.data_ptr()) for p in adapters) + (wf_qkv.data_ptr(),)
+    if cache.get("lora_adapters") != ver:
+        fill_adapters()
+        cache["lora_adapters"] = ver
+    return packs
+
+
+class LoraAttnBlockFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, meta, cache, ln_w, ln_b, qw, qb, kw, kb, vw, vb, ow, ob, temb,
+                qA, qB, kA, kB, vA, vB, oA, oB, scaling):
+        M, D = x.shape
+        hd = D // meta.H
+        r = qA.shape[0]
+        R3, R1 = _pad8(3 * r), _pad8(r)
+        wf_qkv, wb_qkv, wf_o, wb_o, bqkv = lora_packs(cache, (qw, qb, kw, kb, vw, vb, ow, ob),
+                                                      (qA, qB, kA, kB, vA, vB, oA, oB), scaling)
+        hcat = torch.empty((M, D + R3), device=x.device, dtype=BF16)        # [LN(x) | LN(x) A_cat^T]
+        h = hcat[:, :D]
+        if temb is not None:
+            x_res = torch.empty_like(x)
+            _, mean, rstd = ops.layernorm_fwd(x, ln_w, ln_b, meta.eps, add_rows=temb.detach().reshape(-1, D),
+                                              add_period=meta.add_period, add_div=meta.add_div, x_out=x_res, out=h)
+        else:
+            x_res = x
+            _, mean, rstd = ops.layernorm_fwd(x, ln_w, ln_b, meta.eps, out=h)
+        ops.gemm(h, wb_qkv[3 * D:], out=hcat[:, D:])                         # T = h A_cat^T          [M, R3]
+        qkvcat = torch.empty((M, 3 * D + R3), device=x.device, dtype=BF16)   # pitch shared with [dqkv | dT]
+        qkv = qkvcat[:, :3 * D]
+        ops.gemm(hcat, wf_qkv, bias=bqkv, scale_cols=D, col_scale=hd ** -0.5, out=qkv)
+        attncat = torch.empty((M, D + R1), device=x.device, dtype=BF16)      # [attn | attn A_o^T]
+        attn = attncat[:, :D]
+        _, lse = ops.attention_fwd(qkv, meta.layout, meta.H, causal=meta.causal, key_mask=meta.key_mask,
+                                   mask_rows=meta.mask_rows, mask_div=meta.mask_div, out=attn)
+        ops.gemm(attn, wb_o[D:], out=attncat[:, D:])
+        out = ops.gemm(attncat, wf_o, bias=ob.detach(), epilogue=EPI_RESID, aux_in=x_res, out_dtype=F32)
+        ctx.meta, ctx.has_temb, ctx.r, ctx.scaling = meta, temb is not None, r, scaling
+        ctx.save_for_backward(x_res, mean, rstd, hcat, qkvcat, attncat, lse, wf_qkv, wb_qkv, wf_o, wb_o, ln_w)
+        return out
+
+    @staticmethod
+    def backward(ctx, d_out):
+        x_res, mean, rstd, hcat, qkvcat, attncat, lse, wf_qkv, wb_qkv, wf_o, wb_o, ln_w = ctx.saved_tensors
+        meta, r, s = ctx.meta, ctx.r, ctx.scaling
+        M, D = x_res.shape
+        hd = D // meta.H
+        R3, R1 = _pad8(3 * r), _pad8(r)
+        need = ctx.needs_input_grad
+        base_grads = any(need[5:13])                       # somebody un-froze the encoder's own weights
+        h, qkv, attn = hcat[:, :D], qkvcat[:, :3 * D], attncat[:, :D]
+        d_out = _contig(d_out)
+        _GRAD_BF16.pop(d_out.data_ptr(), None)
+        # ---- out_proj group: [dY | dY sB_o] ----
+        dycat = ops.cast_bf16(d_out, cols_dst=D + R1)
+        dy = dycat[:, :D]
+        ops.gemm(dy, wf_o[:, D:], b_mn=True, out=dycat[:, D:])                               # dT_o = dY (sB_o)
+        d_attncat = torch.empty((M, D + R1), device=d_out.device, dtype=BF16)                # pitch of attn
+        d_attn = d_attncat[:, :D]
+        ops.gemm(dycat, wb_o, b_mn=True, out=d_attn)                                         # dY W_o + dT_o A_o
+        d_oA = ops.gemm(dycat[:, D:], attn, a_mn=True, b_mn=True, out_dtype=F32)[:r]         # dT_o^T attn
+        d_oB = ops.gemm(dy, attncat[:, D:], a_mn=True, b_mn=True, out_dtype=F32)[:, :r] * s  # dY^T T_o
+        d_ow = d_ob = None
+        if base_grads:
+            d_ow = ops.gemm(dy, attn, a_mn=True, b_mn=True, out_dtype=F32)
+            d_ob = ops.colsum(dy)
+        # ---- attention core ----
+        dqkvcat = torch.empty((M, 3 * D + R3), device=d_out.device, dtype=BF16)
+        dqkv = dqkvcat[:, :3 * D]
+        _, d_bqkv = ops.attention_bwd(qkv, attn, lse, d_attn, meta.layout, meta.H, hd ** -0.5, causal=meta.causal,
+                                      key_mask=meta.key_mask, mask_rows=meta.mask_rows, mask_div=meta.mask_div,
+                                      dqkv_out=dqkv, want_colsum=base_grads)
+        # ---- q / k / v group: [dqkv | dqkv sB_cat] ----
+        ops.gemm(dqkv, wf_qkv[:, D:], b_mn=True, out=dqkvcat[:, 3 * D:])                     # dT      [M, R3]
+        d_h = ops.gemm(dqkvcat, wb_qkv, b_mn=True)                                           # dqkv W + dT A_cat
+        d_acat = ops.gemm(dqkvcat[:, 3 * D:], h, a_mn=True, b_mn=True, out_dtype=F32)        # [R3, D]
+        d_sb = ops.gemm(dqkv, hcat[:, D:], a_mn=True, b_mn=True, out_dtype=F32)              # [3D, R3]
+        d_A = [d_acat[i * r:(i + 1) * r] for i in range(3)]
+        d_B = [d_sb[i * D:(i + 1) * D, i * r:(i + 1) * r] * s for i in range(3)]
+        d_w = [None] * 3
+        d_b = [None] * 3
+        if base_grads:
+            d_wqkv = ops.gemm(dqkv, h, a_mn=True, b_mn=True, out_dtype=F32)
+            d_w = [d_wqkv[i * D:(i + 1) * D] for i in range(3)]
+            d_b = [d_bqkv[i * D:(i + 1) * D] for i in range(3)]
+        dx, dx_b, d_lnw, d_lnb, dx_cs = ops.layernorm_bwd(d_h, x_res, mean, rstd, ln_w, dres=d_out, want_bf16=True)
+        _publish_bf16(dx, dx_b, dx_cs)
+        d_temb = None
+        if ctx.has_temb:
+            d_temb = ops.colsum_grouped(dx, meta.add_period, meta.add_div).view(1, meta.add_period, D)
+        return (dx, None, None, d_lnw, d_lnb, d_w[0], d_b[0], d_w[1], d_b[1], d_w[2], d_b[2], d_ow, d_ob, d_temb,
+                d_A[0], d_B[0], d_A[1], d_B[1], d_A[2], d_B[2], d_oA, d_oB, None)
 
 
 # ------------------------------------------------------------------------------------------
@@ -184,6 +334,12 @@ class MlpBlockFn(torch.autograd.Function):
         x, mean, rstd, h, u, a, w1b, w2b, ln_w = ctx.saved_tensors
         d_out = _contig(d_out)
         d_out_b, d_b2 = _bf16_of(d_out)
+        if not any(ctx.needs_input_grad[5:9]):             # frozen MLP (peft-wrapped encoder): dgrad only
+            d_u = ops.gemm(d_out_b, w2b, b_mn=True, epilogue=EPI_DGELU, aux_in=u)
+            d_h = ops.gemm(d_u, w1b, b_mn=True)
+            dx, dx_b, d_lnw, d_lnb, dx_cs = ops.layernorm_bwd(d_h, x, mean, rstd, ln_w, dres=d_out, want_bf16=True)
+            _publish_bf16(dx, dx_b, dx_cs)
+            return dx, None, None, d_lnw, d_lnb, None, None, None, None
         d_w2 = ops.gemm(d_out_b, a, a_mn=True, b_mn=True, out_dtype=F32)
         if _AB_DGELU_COLSUM:
             d_b1 = torch.zeros((u.shape[1],), device=u.device, dtype=F32)
@@ -353,6 +509,19 @@ def _pick(bf16_fn, f32_name):
 
 def attn_block(*args):
     return _pick(AttnBlockFn, "AttnBlockF32Fn").apply(*args)
+
+
+def lora_attn_block(x, meta, cache, ln_w, ln_b, qw, qb, kw, kb, vw, vb, ow, ob, temb,
+                    qA, qB, kA, kB, vA, vB, oA, oB, scaling):
+    if get_precision() == "fp32":
+        # verification mode: the adapter folded into an effective fp32 weight W + s B A (exact in fp32; torch
+        # autograd carries dW_eff back to A and B -- [D, r] parameter-space products, not a performance path)
+        from . import autograd_f32
+        eff = [w + scaling * (B @ A) for w, A, B in ((qw, qA, qB), (kw, kA, kB), (vw, vA, vB), (ow, oA, oB))]
+        return autograd_f32.AttnBlockF32Fn.apply(x, meta, {}, ln_w, ln_b, eff[0], qb, eff[1], kb, eff[2], vb,
+                                                 eff[3], ob, temb)
+    return LoraAttnBlockFn.apply(x, meta, cache, ln_w, ln_b, qw, qb, kw, kb, vw, vb, ow, ob, temb,
+                                 qA, qB, kA, kB, vA, vB, oA, oB, scaling)
 
 
 def mlp_block(*args):

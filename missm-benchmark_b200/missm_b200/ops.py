@@ -118,11 +118,14 @@ def _attn_args(qkv, out, lse, lay, H, causal, key_mask, mask_rows, mask_div):
     return a
 
 
-def attention_fwd(qkv, lay, H, *, causal=False, key_mask=None, mask_rows=None, mask_div=1):
-    """qkv bf16 [rows, 3D] (q pre-scaled) -> (out bf16 [rows, D], lse f32 [n_seq, H, N])."""
+def attention_fwd(qkv, lay, H, *, causal=False, key_mask=None, mask_rows=None, mask_div=1, out=None):
+    """qkv bf16 [rows, 3D] (q pre-scaled) -> (out bf16 [rows, D], lse f32 [n_seq, H, N]).  `qkv` / `out` may be
+    column views of wider row-major buffers (pitch a multiple of 8 elements)."""
     assert qkv.dtype == BF16 and qkv.is_cuda
     D = qkv.shape[1] // 3
-    out = torch.empty((qkv.shape[0], D), device=qkv.device, dtype=BF16)
+    if out is None:
+        out = torch.empty((qkv.shape[0], D), device=qkv.device, dtype=BF16)
+    assert out.dtype == BF16 and out.shape == (qkv.shape[0], D)
     lse = torch.empty((lay.n_seq, H, lay.N), device=qkv.device, dtype=F32)
     a = _attn_args(qkv, out, lse, lay, H, causal, key_mask, mask_rows, mask_div)
     LAUNCHES[0] += 1
@@ -131,12 +134,17 @@ def attention_fwd(qkv, lay, H, *, causal=False, key_mask=None, mask_rows=None, m
 
 
 def attention_bwd(qkv, out, lse, d_out, lay, H, q_scale, *, causal=False, key_mask=None,
-                  mask_rows=None, mask_div=1):
+                  mask_rows=None, mask_div=1, dqkv_out=None, want_colsum=True):
     """-> (dqkv bf16 [rows, 3D], column sums of dqkv f32 [3D] = the q/k/v bias gradients); the q block is
     the gradient w.r.t. the UN-scaled projection.  (Emitting the column sums from the kernels' epilogues
     was measured slower -- contended atomics -- so one extra HBM-bound pass over dqkv computes them.)"""
     assert d_out.dtype == BF16 and d_out.shape == out.shape and _ld(d_out) == _ld(out)
-    dqkv = torch.empty_like(qkv)
+    if dqkv_out is None:
+        dqkv = torch.empty(qkv.shape, device=qkv.device, dtype=BF16) if _ld(qkv) == qkv.shape[1] else None
+        assert dqkv is not None, "a strided qkv view needs dqkv_out with the same pitch"
+    else:
+        dqkv = dqkv_out
+        assert dqkv.dtype == BF16 and dqkv.shape == qkv.shape and _ld(dqkv) == _ld(qkv)
     delta = torch.empty_like(lse)
     a = _attn_args(qkv, out, lse, lay, H, causal, key_mask, mask_rows, mask_div)
     a.d_out, a.delta, a.dqkv, a.q_scale = d_out.data_ptr(), delta.data_ptr(), dqkv.data_ptr(), q_scale
@@ -144,19 +152,24 @@ def attention_bwd(qkv, out, lse, d_out, lay, H, q_scale, *, causal=False, key_ma
     a.colsum_done = 0
     LAUNCHES[0] += 3
     check(lib().missm_attention_bwd(ctypes.byref(a), stream_ptr()), "attention_bwd")
-    if not a.colsum_done:
+    if want_colsum and not a.colsum_done:
         csum = colsum(dqkv)
     return dqkv, csum
 
 
 # ---------------------------------------------------------------------------------- layernorm
 def layernorm_fwd(x, gamma, beta, eps, *, out_dtype=BF16, row_index=None, n_rows=None,
-                  add_rows=None, add_period=0, add_div=0, x_out=None, want_stats=True):
-    """x f32 [R, D] -> (y [M, D], mean [M], rstd [M]); M = len(row_index) or R."""
+                  add_rows=None, add_period=0, add_div=0, x_out=None, want_stats=True, out=None):
+    """x f32 [R, D] -> (y [M, D], mean [M], rstd [M]); M = len(row_index) or R.  `out`: write y into this
+    row-major (possibly wider-pitched) [M, D] view instead of a fresh tensor."""
     assert x.dtype == F32 and x.is_cuda
     D = x.shape[1]
     M = n_rows if n_rows is not None else (row_index.numel() if row_index is not None else x.shape[0])
-    y = torch.empty((M, D), device=x.device, dtype=out_dtype)
+    if out is not None:
+        assert out.shape == (M, D) and out.dtype == out_dtype
+        y = out
+    else:
+        y = torch.empty((M, D), device=x.device, dtype=out_dtype)
     mean = torch.empty((M,), device=x.device, dtype=F32) if want_stats else None
     rstd = torch.empty((M,), device=x.device, dtype=F32) if want_stats else None
     LAUNCHES[0] += 1

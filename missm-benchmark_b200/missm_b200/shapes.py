@@ -10,7 +10,7 @@ from .bank import LanguageBind
 
 _VISION_KEYS = ("hidden_size", "intermediate_size", "num_hidden_layers", "num_attention_heads", "num_channels",
                 "image_size", "patch_size", "hidden_act", "layer_norm_eps", "add_time_attn", "num_frames",
-                "num_mel_bins", "target_length")
+                "num_mel_bins", "target_length", "lora_r", "lora_alpha", "lora_dropout")
 _TEXT_KEYS = ("vocab_size", "hidden_size", "intermediate_size", "num_hidden_layers", "num_attention_heads",
               "max_position_embeddings", "hidden_act", "layer_norm_eps")
 
@@ -30,7 +30,7 @@ def build_bank(vision_cfgs, text_cfg, projection_dim=768, use_temp=True):
     for m, vc in vision_cfgs.items():
         cls = mods[m]
         vd = _as_dict(vc, _VISION_KEYS)
-        vd["lora_r"] = 0
+        vd.setdefault("lora_r", 0)      # the builders default to the plain encoder (reference default: 2)
         cfg = cls.config_class(text_config=_as_dict(text_cfg, _TEXT_KEYS), vision_config=vd,
                                projection_dim=projection_dim)
         models[m] = cls(cfg)

@@ -36,8 +36,61 @@ def _require_cuda(t, what):
                            f"(move the model and its inputs to a CUDA device)")
 
 
+class LoraLinear(nn.Linear):
+    """Parameter container of a peft-wrapped Linear (peft 0.4/0.5 layout: the wrapper IS the nn.Linear, so the
+    frozen `weight` / `bias` keep their names, plus `lora_A.default.weight` [r, in] and `lora_B.default.weight`
+    [out, r]); y = W x + b + (lora_alpha / r) B(A(x)).  Created by convert_to_lora below (reference:
+    modeling_image.py:775-793).  Initialised as peft does: A kaiming-uniform(a = sqrt 5), B = 0."""
+
+    def __init__(self, in_features, out_features, r, lora_alpha, lora_dropout):
+        super().__init__(in_features, out_features)
+        self.r, self.scaling, self.p_drop = int(r), float(lora_alpha) / float(r), float(lora_dropout)
+        self.lora_A = nn.ModuleDict({'default': nn.Linear(in_features, r, bias=False)})
+        self.lora_B = nn.ModuleDict({'default': nn.Linear(r, out_features, bias=False)})
+        nn.init.kaiming_uniform_(self.lora_A['default'].weight, a=math.sqrt(5))
+        nn.init.zeros_(self.lora_B['default'].weight)
+
+    @property
+    def A(self):
+        return self.lora_A['default'].weight
+
+    @property
+    def B(self):
+        return self.lora_B['default'].weight
+
+
+class _Wrapped(nn.Module):
+    """peft's two wrapper levels, kept only for the parameter NAMES they produce
+    (`encoder.base_model.model.layers.N...`): PeftModel.base_model = LoraModel, LoraModel.model = CLIPEncoder."""
+    _inner = None
+
+    def __getattr__(self, name):
+        try:
+            return super().__getattr__(name)
+        except AttributeError:
+            if name == self._inner:
+                raise
+            return getattr(super().__getattr__(self._inner), name)
+
+
+class LoraModel(_Wrapped):
+    _inner = 'model'
+
+    def __init__(self, model):
+        super().__init__()
+        self.model = model
+
+
+class PeftModel(_Wrapped):
+    _inner = 'base_model'
+
+    def __init__(self, model):
+        super().__init__()
+        self.base_model = LoraModel(model)
+
+
 class CLIPAttention(nn.Module):
-    def __init__(self, config):
+    def __init__(self, config, lora=None):
         super().__init__()
         d = config.hidden_size
         self.embed_dim, self.num_heads = d, config.num_attention_heads
@@ -47,10 +100,19 @@ class CLIPAttention(nn.Module):
         if config.attention_dropout != 0.0:
             raise NotImplementedError("attention_dropout != 0 is not built (reference default 0.0, "
                                       "configuration_image.py:193)")
-        self.k_proj = nn.Linear(d, d)
-        self.v_proj = nn.Linear(d, d)
-        self.q_proj = nn.Linear(d, d)
-        self.out_proj = nn.Linear(d, d)
+        lin = (lambda: nn.Linear(d, d)) if not lora else (lambda: LoraLinear(d, d, *lora))
+        self.has_lora = bool(lora)
+        self.k_proj = lin()
+        self.v_proj = lin()
+        self.q_proj = lin()
+        self.out_proj = lin()
+
+    def lora_params(self):
+        """(A, B) of q, k, v, out in the order autograd.LoraAttnBlockFn takes them, then the scaling."""
+        out = []
+        for m in (self.q_proj, self.k_proj, self.v_proj, self.out_proj):
+            out += [m.A, m.B]
+        return out + [self.q_proj.scaling]
 
 
 class CLIPMLP(nn.Module):
@@ -69,7 +131,13 @@ class CLIPEncoderLayer(nn.Module):
         d = config.hidden_size
         self.embed_dim = d
         self.eps = config.layer_norm_eps
-        self.self_attn = CLIPAttention(config)
+        # convert_to_lora (modeling_image.py:775-793): with temporal attention the adapters sit on temporal_attn.*
+        # (and temporal_mlp.fc1 / fc2 where that block exists), otherwise on every *.{q,k,v,out}_proj
+        lora = None
+        if getattr(config, 'lora_r', 0):
+            lora = (config.lora_r, config.lora_alpha, config.lora_dropout)
+        time_attn = bool(getattr(config, 'add_time_attn', False))
+        self.self_attn = CLIPAttention(config, None if time_attn else lora)
         self.layer_norm1 = nn.LayerNorm(d, eps=config.layer_norm_eps)
         self.mlp = CLIPMLP(config)
         self.layer_norm2 = nn.LayerNorm(d, eps=config.layer_norm_eps)
@@ -79,8 +147,11 @@ class CLIPEncoderLayer(nn.Module):
             self.t = config.num_frames
             self.temporal_embedding = nn.Parameter(torch.zeros(1, config.num_frames, d))
             nn.init.normal_(self.temporal_embedding, std=d ** -0.5)
-            self.temporal_attn = CLIPAttention(config)
+            self.temporal_attn = CLIPAttention(config, lora)
             self.temporal_layer_norm1 = nn.LayerNorm(d, eps=config.layer_norm_eps)
+            if temporal_mlp and lora:
+                raise NotImplementedError("LoRA on temporal_mlp.fc1 / fc2 (modeling_image.py:780-781) is not built: "
+                                          "only the video tower enables temporal attention, and it has no temporal MLP")
             if temporal_mlp:   # image/audio/depth/thermal files keep it (:83-84), video dropped it
                 self.has_temporal_mlp = True
                 self.temporal_mlp = CLIPMLP(config)
@@ -92,19 +163,25 @@ class CLIPEncoderLayer(nn.Module):
         return (ln.weight, ln.bias, a.q_proj.weight, a.q_proj.bias, a.k_proj.weight, a.k_proj.bias,
                 a.v_proj.weight, a.v_proj.bias, a.out_proj.weight, a.out_proj.bias)
 
+    def _attn(self, x, meta, cache, ln, a, temb):
+        if a.has_lora:
+            if a.q_proj.p_drop != 0.0 and self.training:
+                raise NotImplementedError("lora_dropout != 0 in training mode is not built (reference default 0.0, "
+                                          "configuration_image.py:202)")
+            return ag.lora_attn_block(x, meta, cache, *self._attn_params(ln, a), temb, *a.lora_params())
+        return ag.attn_block(x, meta, cache, *self._attn_params(ln, a), temb)
+
     def run(self, x, spatial_meta, temporal_meta):
         """x: fp32 [M, D] residual stream, rows ordered (image, token)."""
         if self.add_time_attn:
             temb = self.temporal_embedding if self.t != 1 else None
-            x = ag.attn_block(x, temporal_meta, self._cache["ta"],
-                                     *self._attn_params(self.temporal_layer_norm1, self.temporal_attn), temb)
+            x = self._attn(x, temporal_meta, self._cache["ta"], self.temporal_layer_norm1, self.temporal_attn, temb)
             if self.has_temporal_mlp:
                 m = self.temporal_mlp
                 x = ag.mlp_block(x, self.eps, self._cache["tmlp"], self.temporal_layer_norm2.weight,
                                         self.temporal_layer_norm2.bias, m.fc1.weight, m.fc1.bias,
                                         m.fc2.weight, m.fc2.bias)
-        x = ag.attn_block(x, spatial_meta, self._cache["sa"],
-                                 *self._attn_params(self.layer_norm1, self.self_attn), None)
+        x = self._attn(x, spatial_meta, self._cache["sa"], self.layer_norm1, self.self_attn, None)
         m = self.mlp
         x = ag.mlp_block(x, self.eps, self._cache["mlp"], self.layer_norm2.weight, self.layer_norm2.bias,
                                 m.fc1.weight, m.fc1.bias, m.fc2.weight, m.fc2.bias)
@@ -168,12 +245,16 @@ class CLIPVisionTransformer(nn.Module):
         self.config = config
         if config.hidden_size // config.num_attention_heads != 64:
             raise NotImplementedError("the fused attention kernel is built for head_dim 64")
-        if getattr(config, 'lora_r', 0):
-            raise NotImplementedError("lora_r != 0 (peft-wrapped encoder, modeling_image.py:775-793) is the "
-                                      "next row of SURVEY.md section 8(f); build with lora_r=0")
         self.embeddings = CLIPVisionEmbeddings(config, persistent_ids)
         self.pre_layrnorm = nn.LayerNorm(config.hidden_size, eps=config.layer_norm_eps)
         self.encoder = CLIPEncoder(config, temporal_mlp)
+        if getattr(config, 'lora_r', 0):
+            # what get_peft_model does to the encoder (modeling_image.py:793, bias="none"): adapters are the only
+            # trainable parameters inside it, and its parameters move under encoder.base_model.model
+            for n, p in self.encoder.named_parameters():
+                if 'lora_' not in n:
+                    p.requires_grad = False
+            self.encoder = PeftModel(self.encoder)
         self.post_layernorm = nn.LayerNorm(config.hidden_size, eps=config.layer_norm_eps)
         self._cache = {"embed": {}, "pool": {}}
 
@@ -388,15 +469,28 @@ class _LanguageBindModel(nn.Module):
 
     def load_reference_state_dict(self, sd):
         """Load a reference/hub state dict by name; position tables of another grid are resampled the
-        way resize_pos does, `position_ids` buffers are ignored."""
-        sd = {k: v for k, v in sd.items() if not k.endswith("position_ids")}
-        if any(".lora_" in k or k.startswith("vision_model.encoder.base_model") for k in sd):
-            raise NotImplementedError("LoRA-wrapped checkpoints (SURVEY.md section 8(f) rank 1)")
+        way resize_pos does, `position_ids` buffers are ignored.  Encoder keys are accepted in the three layouts a
+        reference checkpoint can have: plain (`vision_model.encoder.layers.N...`,
+        lora_r = 0 or adapters merged before saving), peft-wrapped in the 0.4/0.5 layout this module tree uses
+        (`vision_model.encoder.base_model.model.layers.N...q_proj.weight` + `.lora_A.default.weight`), and the
+        peft >= 0.6 layout of the same thing (`...q_proj.base_layer.weight`).  A plain checkpoint loads into a
+        LoRA-configured model with the adapters left at their no-op initialisation (B = 0)."""
+        sd = {k.replace(".base_layer.", "."): v for k, v in sd.items() if not k.endswith("position_ids")}
+        wrapped = isinstance(self.vision_model.encoder, PeftModel)
+        plain_p, peft_p = "vision_model.encoder.", "vision_model.encoder.base_model.model."
+        has_peft_keys = any(k.startswith(peft_p) for k in sd)
+        keep_adapters = False
+        if wrapped and not has_peft_keys:
+            sd = {(peft_p + k[len(plain_p):] if k.startswith(plain_p) else k): v for k, v in sd.items()}
+            keep_adapters = True
+        elif has_peft_keys and not wrapped:
+            raise RuntimeError("the checkpoint holds a peft-wrapped encoder (LoRA adapters) but the model was built "
+                               "with lora_r = 0: build it from the checkpoint's own config.json")
         k = "vision_model.embeddings.position_embedding.weight"
         if k in sd and sd[k].shape[0] != self.vision_model.embeddings.num_positions:
             sd[k] = resize_pos_table(sd[k], self.vision_model.embeddings.grid)
         missing, unexpected = self.load_state_dict(sd, strict=False)
-        missing = [m for m in missing if not m.endswith("position_ids")]
+        missing = [m for m in missing if not m.endswith("position_ids") and not (keep_adapters and ".lora_" in m)]
         if missing or unexpected:
             raise RuntimeError(f"state dict mismatch: missing={missing[:5]} unexpected={unexpected[:5]}")
 

@@ -138,6 +138,59 @@ def tiny():
                                   for k, v in out.items() if not k.startswith('grad/')})
 
 
+LORA_V = dict(TINY_V, lora_r=2, lora_alpha=16)
+LORA_PER = {'video': dict(add_time_attn=True, num_frames=4)}
+LORA_MODALS = ['video', 'image']
+
+
+def lora():
+    """peft-wrapped encoders (the reference config DEFAULT is lora_r = 2,
+    configuration_image.py:200).  The reference's own convert_to_lora (modeling_image.py:775-793) runs against the
+    peft restatement of ref_shim.py: spatial LoRA on the image tower, temporal-attention LoRA on the video tower,
+    frozen encoder weights, a trained (non-zero B) adapter; fwd + bwd of the `sum` head."""
+    torch.manual_seed(0)
+    bank = ref_shim.build_reference_bank(LORA_MODALS, LORA_V, TINY_T, projection_dim=64, per_modality_cfg=LORA_PER)
+    cfgs = {}
+    for m in LORA_MODALS:
+        d = dict(LORA_V)
+        d.update(LORA_PER.get(m, {}))
+        d['temporal_mlp'] = (m != 'video')
+        cfgs[m] = R.vision_config(**d)
+    tcfg = R.text_config(**TINY_T)
+    modal_types = ['language'] + LORA_MODALS
+    B = 5
+    data = R.synth_inputs(modal_types, B, cfgs, tcfg, seed=3)
+    missing_index = torch.tensor([0, 4, 2, 0, 1], dtype=torch.long)
+    model = ref_shim.build_reference_model(bank, 'sum', modal_types, 3, feature_dims=64, fusion_dim=32,
+                                           dropout_prob=0.0, extra_missing_codes={'depth': 5, 'thermal': 6})
+    names = {k: tuple(v.shape) for k, v in model.state_dict().items()}
+    load_synth(model)
+    out = {'meta': dict(vision=LORA_V, text=TINY_T, per=LORA_PER, modals=LORA_MODALS, projection_dim=64, B=B,
+                        fusion_dim=32, n_classes=3, seed=3),
+           'missing_index': missing_index, 'names': names,
+           'trainable': [n for n, p in model.named_parameters() if p.requires_grad]}
+    model.eval()
+    with torch.no_grad():
+        emb = model.encoder({k: dict(v) for k, v in data.items()})
+        out['logits/sum'] = model({k: dict(v) for k, v in data.items()}, missing_index).clone()
+    for k, v in emb.items():
+        out[f'emb/{k}'] = v.clone()
+    model.train()
+    labels = torch.tensor([0, 1, 2, 0, 1])
+    loss = torch.nn.functional.cross_entropy(model({k: dict(v) for k, v in data.items()}, missing_index), labels)
+    loss.backward()
+    out['labels'], out['loss/sum'] = labels, loss.detach().clone()
+    gn = {}
+    for n, p in model.named_parameters():
+        gn[n] = float(p.grad.norm()) if p.grad is not None else None
+        if p.grad is not None and ('lora_' in n or 'embeddings' in n or 'layrnorm' in n):
+            out[f'grad/{n}'] = p.grad.detach().clone()
+    out['grad_norms'] = gn
+    torch.save(out, os.path.join(GOLD, 'tiny_lora.pt'))
+    print('lora golden written: %d trainable / %d parameters, %d gradient tensors' %
+          (len(out['trainable']), len(gn), sum(k.startswith('grad/') for k in out)))
+
+
 def full():
     """BASELINE.json config 1: image ViT-L/14 224 + text, forward, B = 8, one image-missing
     sample, CPU fp32; plus a B = 4 fwd+bwd step (loss and gradient norms)."""
@@ -183,8 +236,12 @@ def full():
 if __name__ == '__main__':
     ap = argparse.ArgumentParser()
     ap.add_argument('--full', action='store_true')
+    ap.add_argument('--only-lora', action='store_true')
     a = ap.parse_args()
     os.makedirs(GOLD, exist_ok=True)
+    lora()
+    if a.only_lora:
+        sys.exit(0)
     tiny()
     if a.full:
         full()

@@ -6,7 +6,7 @@ It never travels to the GPU box and nothing in the product path imports it.
 
 Why a shim is needed: the reference binds third-party
 names at import time (languagebind/image/modeling_image.py:5-15) that do not exist in this
-image: `peft`, `decord`, `pytorchvideo`, `torch_geometric`, and four symbols of a
+image: `peft` (LoRA re-stated below), `decord`, `pytorchvideo`, `torch_geometric`, and four symbols of a
 transformers-4.3x-era `modeling_clip` (`_expand_mask`, the 4.3x `CLIPAttention` calling
 convention with `causal_attention_mask=`, and a `CLIPVisionEmbeddings` without the
 square-input check).  The third-party arithmetic is re-stated here from its published
@@ -111,6 +111,78 @@ class CLIPVisionEmbeddings(nn.Module):
         return emb + self.position_embedding(self.position_ids)
 
 
+# ---------------------------------------------------------------------------------------------
+# peft (third-party, unpinned by the reference, not installed here): LoRA re-stated from its published
+# algorithm (peft 0.4/0.5 layout, contemporary with the transformers 4.31-4.34 API the reference needs):
+#   get_peft_model(model, LoraConfig) -> PeftModel(base_model=LoraModel(model=model)); every nn.Linear
+#   whose qualified name ends with a target is replaced by a Linear subclass that keeps `weight`/`bias`
+#   and adds lora_A.default [r, in] (kaiming-uniform, a = sqrt 5), lora_B.default [out, r] (zeros):
+#   y = W x + b + (lora_alpha / r) * B(A(dropout(x)));  bias="none": every parameter without "lora_" in its
+#   name is frozen.  Call site: modeling_image.py:775-793 (`convert_to_lora`).
+# ---------------------------------------------------------------------------------------------
+class LoraConfig:
+    def __init__(self, r=8, lora_alpha=8, target_modules=None, lora_dropout=0.0, bias="none",
+                 modules_to_save=None, **kwargs):
+        self.r, self.lora_alpha, self.target_modules = r, lora_alpha, list(target_modules or [])
+        self.lora_dropout, self.bias, self.modules_to_save = lora_dropout, bias, modules_to_save
+
+
+class LoraLinear(nn.Linear):
+    def __init__(self, base, r, lora_alpha, lora_dropout):
+        super().__init__(base.in_features, base.out_features, bias=base.bias is not None)
+        self.weight, self.bias = base.weight, base.bias
+        self.lora_dropout = nn.ModuleDict({'default': nn.Dropout(lora_dropout) if lora_dropout > 0 else nn.Identity()})
+        self.lora_A = nn.ModuleDict({'default': nn.Linear(base.in_features, r, bias=False)})
+        self.lora_B = nn.ModuleDict({'default': nn.Linear(r, base.out_features, bias=False)})
+        self.scaling = lora_alpha / r
+        nn.init.kaiming_uniform_(self.lora_A['default'].weight, a=5 ** 0.5)
+        nn.init.zeros_(self.lora_B['default'].weight)
+
+    def forward(self, x):
+        y = nn.functional.linear(x, self.weight, self.bias)
+        return y + self.lora_B['default'](self.lora_A['default'](self.lora_dropout['default'](x))) * self.scaling
+
+
+class _Delegate(nn.Module):
+    _inner = None
+
+    def __getattr__(self, name):
+        try:
+            return super().__getattr__(name)
+        except AttributeError:
+            return getattr(super().__getattr__(self._inner), name)
+
+    def forward(self, *a, **k):
+        return getattr(self, self._inner)(*a, **k)
+
+
+class LoraModel(_Delegate):
+    _inner = 'model'
+
+    def __init__(self, model, config):
+        super().__init__()
+        self.model = model
+        for name, mod in list(model.named_modules()):
+            if isinstance(mod, nn.Linear) and any(name == t or name.endswith('.' + t) for t in config.target_modules):
+                parent = model.get_submodule(name.rsplit('.', 1)[0]) if '.' in name else model
+                setattr(parent, name.rsplit('.', 1)[-1], LoraLinear(mod, config.r, config.lora_alpha, config.lora_dropout))
+        for n, p in model.named_parameters():
+            if 'lora_' not in n:
+                p.requires_grad = False
+
+
+class PeftModel(_Delegate):
+    _inner = 'base_model'
+
+    def __init__(self, model, config):
+        super().__init__()
+        self.base_model = LoraModel(model, config)
+
+
+def get_peft_model(model, config):
+    return PeftModel(model, config)
+
+
 _installed = False
 
 
@@ -119,7 +191,7 @@ def install():
     global _installed
     if _installed:
         return
-    _stub("peft", LoraConfig=_Unavailable, get_peft_model=_Unavailable)
+    _stub("peft", LoraConfig=LoraConfig, get_peft_model=get_peft_model)
     _stub("decord", VideoReader=_Unavailable, cpu=lambda *a, **k: None,
           bridge=types.SimpleNamespace(set_bridge=lambda *a, **k: None))
     _stub("pytorchvideo")

@@ -37,7 +37,8 @@ def vision_config(**kw):
     """Defaults of CLIPVisionConfig (languagebind/image/configuration_image.py:180-233)."""
     d = dict(hidden_size=768, intermediate_size=3072, num_hidden_layers=12, num_attention_heads=12,
              num_channels=3, image_size=224, patch_size=32, hidden_act="quick_gelu", layer_norm_eps=1e-5,
-             add_time_attn=False, num_frames=1, num_mel_bins=0, target_length=0, temporal_mlp=True)
+             add_time_attn=False, num_frames=1, num_mel_bins=0, target_length=0, temporal_mlp=True,
+             lora_r=0, lora_alpha=16)      # lora_r: the reference default is 2 (:200); 0 = plain encoder
     d.update(kw)
     return types.SimpleNamespace(**d)
 
@@ -80,13 +81,24 @@ def act_fn(name, x):
     raise ValueError(name)
 
 
-def clip_attention(sd, pre, x, n_heads, causal_mask=None, attn_mask=None):
+def lora_linear(sd, pre, x, scaling):
+    """A Linear that peft may have wrapped (convert_to_lora, modeling_image.py:775-793; peft is third-party,
+    unpinned and absent -- restated from its published algorithm): W x + b + (lora_alpha / r) B(A(x)).
+    lora_dropout is the identity at the reference default 0.0 (configuration_image.py:202) and in eval mode."""
+    y = F.linear(x, sd[pre + 'weight'], sd.get(pre + 'bias'))
+    a = sd.get(pre + 'lora_A.default.weight')
+    if a is not None:
+        y = y + F.linear(F.linear(x, a), sd[pre + 'lora_B.default.weight']) * scaling
+    return y
+
+
+def clip_attention(sd, pre, x, n_heads, causal_mask=None, attn_mask=None, lora_scaling=1.0):
     """transformers 4.3x CLIPAttention.forward."""
     b, n, d = x.shape
     hd = d // n_heads
-    q = F.linear(x, sd[pre + 'q_proj.weight'], sd[pre + 'q_proj.bias']) * hd ** -0.5
-    k = F.linear(x, sd[pre + 'k_proj.weight'], sd[pre + 'k_proj.bias'])
-    v = F.linear(x, sd[pre + 'v_proj.weight'], sd[pre + 'v_proj.bias'])
+    q = lora_linear(sd, pre + 'q_proj.', x, lora_scaling) * hd ** -0.5
+    k = lora_linear(sd, pre + 'k_proj.', x, lora_scaling)
+    v = lora_linear(sd, pre + 'v_proj.', x, lora_scaling)
     sh = lambda t: t.view(b, n, n_heads, hd).transpose(1, 2)
     w = sh(q) @ sh(k).transpose(-1, -2)                      # [b, H, n, n]
     if causal_mask is not None:
@@ -95,13 +107,13 @@ def clip_attention(sd, pre, x, n_heads, causal_mask=None, attn_mask=None):
         w = w + attn_mask
     w = torch.softmax(w, dim=-1)
     o = (w @ sh(v)).transpose(1, 2).reshape(b, n, d)
-    return F.linear(o, sd[pre + 'out_proj.weight'], sd[pre + 'out_proj.bias'])
+    return lora_linear(sd, pre + 'out_proj.', o, lora_scaling)
 
 
-def clip_mlp(sd, pre, x, act):
-    """transformers CLIPMLP.forward: fc2(act(fc1(x)))."""
-    h = act_fn(act, F.linear(x, sd[pre + 'fc1.weight'], sd[pre + 'fc1.bias']))
-    return F.linear(h, sd[pre + 'fc2.weight'], sd[pre + 'fc2.bias'])
+def clip_mlp(sd, pre, x, act, lora_scaling=1.0):
+    """transformers CLIPMLP.forward: fc2(act(fc1(x))) (temporal_mlp.fc1 / fc2 are LoRA targets, modeling_image.py:780-781)."""
+    h = act_fn(act, lora_linear(sd, pre + 'fc1.', x, lora_scaling))
+    return lora_linear(sd, pre + 'fc2.', h, lora_scaling)
 
 
 def layer_norm(sd, pre, x, eps):
@@ -111,6 +123,7 @@ def layer_norm(sd, pre, x, eps):
 def encoder_layer(sd, pre, x, cfg, causal_mask=None, attn_mask=None):
     """CLIPEncoderLayer.forward (modeling_image.py:86-158; video :192-264)."""
     H, eps, act = cfg.num_attention_heads, cfg.layer_norm_eps, cfg.hidden_act
+    ls = cfg.lora_alpha / cfg.lora_r if getattr(cfg, 'lora_r', 0) else 1.0
     if getattr(cfg, 'add_time_attn', False):
         bt, n, d = x.shape
         t = cfg.num_frames
@@ -120,16 +133,16 @@ def encoder_layer(sd, pre, x, cfg, causal_mask=None, attn_mask=None):
             x = to_space(to_time(x) + sd[pre + 'temporal_embedding'][:, :t, :])
         res = x
         h = layer_norm(sd, pre + 'temporal_layer_norm1.', to_time(x), eps)
-        h = clip_attention(sd, pre + 'temporal_attn.', h, H, causal_mask, attn_mask)
+        h = clip_attention(sd, pre + 'temporal_attn.', h, H, causal_mask, attn_mask, ls)
         x = res + to_space(h)
         if cfg.temporal_mlp:          # image/audio/depth/thermal variant; commented out for video
             res = x
             h = layer_norm(sd, pre + 'temporal_layer_norm2.', to_time(x), eps)
-            h = clip_mlp(sd, pre + 'temporal_mlp.', h, act)
+            h = clip_mlp(sd, pre + 'temporal_mlp.', h, act, ls)
             x = res + to_space(h)
     res = x
     h = layer_norm(sd, pre + 'layer_norm1.', x, eps)
-    x = res + clip_attention(sd, pre + 'self_attn.', h, H, causal_mask, attn_mask)
+    x = res + clip_attention(sd, pre + 'self_attn.', h, H, causal_mask, attn_mask, ls)
     res = x
     h = layer_norm(sd, pre + 'layer_norm2.', x, eps)
     return res + clip_mlp(sd, pre + 'mlp.', h, act)
@@ -149,8 +162,10 @@ def vision_tower(sd, pre, pixel_values, cfg):
     x = torch.cat([cls, pe], dim=1) + sd[pre + 'embeddings.position_embedding.weight'][None]
     # PatchDropout is the identity at force_patch_dropout = 0 (modeling_image.py:31-32)
     x = layer_norm(sd, pre + 'pre_layrnorm.', x, cfg.layer_norm_eps)
+    # a peft-wrapped encoder (lora_r != 0) keeps its layers under encoder.base_model.model (modeling_image.py:793)
+    enc = f'{pre}encoder.base_model.model.' if getattr(cfg, 'lora_r', 0) else f'{pre}encoder.'
     for i in range(cfg.num_hidden_layers):
-        x = encoder_layer(sd, f'{pre}encoder.layers.{i}.', x, cfg)
+        x = encoder_layer(sd, f'{enc}layers.{i}.', x, cfg)
     pooled = layer_norm(sd, pre + 'post_layernorm.', x[:, 0, :], cfg.layer_norm_eps)
     return pooled.reshape(B, T, -1).mean(1)
 
@@ -325,6 +340,9 @@ def synth_state_dict(named_shapes):
             sd[name] = 1.0 + synth_param(name, shape, 0.1)
         elif leaf == 'bias' or 'in_proj_bias' in name:
             sd[name] = synth_param(name, shape, 0.02)
+        elif 'lora_B' in name:
+            # peft initialises B = 0 (the adapter is a no-op); a trained adapter is what needs checking
+            sd[name] = synth_param(name, shape, 0.05 * shape[1] ** -0.5)
         elif 'statistics_' in name:
             sd[name] = synth_param(name, shape, 0.05)
         elif len(shape) >= 2:

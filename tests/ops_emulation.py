@@ -23,10 +23,11 @@ def _gelu_grad(x):
 
 
 # ------------------------------------------------------------------ missm_gemm_bf16 (bf16 operands, fp32 accumulate)
-def gemm(a, b, *, a_mn=False, b_mn=False, out=None, out_dtype=BF16, bias=None, epilogue=EPI_LINEAR, aux_in=None,
+def gemm(a, b, *, a_mn=False, b_mn=False, out=None, out_dtype=None, bias=None, epilogue=EPI_LINEAR, aux_in=None,
          aux_out=None, scale_cols=0, col_scale=1.0, patch_P=0, out_rows=None, split_k=0, force_bn=0,
          colsum_out=None):
     assert a.dtype == BF16 and b.dtype == BF16
+    out_dtype = BF16 if out_dtype is None else out_dtype
     A = (a.t() if a_mn else a).double()
     Bm = (b.t() if b_mn else b).double()
     assert A.shape[1] == Bm.shape[1], (A.shape, Bm.shape)
@@ -127,8 +128,9 @@ def attention_f32_bwd(qkv, out, lse, d_out, lay, H, q_scale, *, causal=False, ke
 
 
 # ------------------------------------------------------------------ layernorm
-def layernorm_fwd(x, gamma, beta, eps, *, out_dtype=BF16, row_index=None, n_rows=None, add_rows=None, add_period=0,
-                  add_div=0, x_out=None, want_stats=True):
+def layernorm_fwd(x, gamma, beta, eps, *, out_dtype=None, row_index=None, n_rows=None, add_rows=None, add_period=0,
+                  add_div=0, x_out=None, want_stats=True, out=None):
+    out_dtype = BF16 if out_dtype is None else out_dtype
     xs = x
     if row_index is not None:
         xs = x[row_index[:n_rows].long() if n_rows is not None else row_index.long()]
@@ -142,6 +144,10 @@ def layernorm_fwd(x, gamma, beta, eps, *, out_dtype=BF16, row_index=None, n_rows
     var = ((xs - mean[:, None]) ** 2).mean(-1)
     rstd = (var + eps).rsqrt()
     y = ((xs - mean[:, None]) * rstd[:, None] * gamma.detach() + beta.detach()).to(out_dtype)
+    if out is not None:
+        assert out.shape == y.shape and out.dtype == out_dtype
+        out.copy_(y)
+        y = out
     return y, mean, rstd
 
 
@@ -153,11 +159,17 @@ def layernorm_bwd(dy, x, mean, rstd, gamma, *, dres=None, row_index=None, dx=Non
     d = rstd[:, None] * (g - g.mean(-1, keepdim=True) - xhat * (g * xhat).mean(-1, keepdim=True))
     if dres is not None:
         d = d + dres
+    b16 = dx_bf16
     if row_index is None:
         dx = d
+        if want_bf16 or dx_bf16 is not None:
+            b16 = d.to(BF16)
     else:
-        dx[row_index[:dy.shape[0]].long()] = d
-    return dx, None, (dyf * xhat).sum(0), dyf.sum(0), d.sum(0)
+        rows = row_index[:dy.shape[0]].long()
+        dx[rows] = d
+        if dx_bf16 is not None:
+            dx_bf16[rows] = d.to(BF16)
+    return dx, b16, (dyf * xhat).sum(0), dyf.sum(0), d.sum(0)
 
 
 # ------------------------------------------------------------------ small kernels
@@ -205,10 +217,12 @@ def cls_rows(cls, pos, tok, Bn, ntok):
 
 
 def embed_bwd(dtok, Bn, ntok):
-    return dtok.reshape(Bn, ntok, -1).sum(0), None
+    d = dtok.reshape(Bn, ntok, -1)
+    return d.sum(0), d[:, 1:].reshape(Bn * (ntok - 1), -1).to(BF16)
 
 
-def frame_mean(x, Bn, T, out_dtype=BF16):
+def frame_mean(x, Bn, T, out_dtype=None):
+    out_dtype = BF16 if out_dtype is None else out_dtype
     return x.reshape(Bn, T, -1).mean(1).to(out_dtype)
 
 
@@ -221,7 +235,8 @@ def l2norm_scale_fwd(x, scale):
     return x * inv[:, None] * scale, inv
 
 
-def l2norm_scale_bwd(dy, x, inv, scale, out_dtype=BF16):
+def l2norm_scale_bwd(dy, x, inv, scale, out_dtype=None):
+    out_dtype = BF16 if out_dtype is None else out_dtype
     yh = x * inv[:, None]
     return (scale * inv[:, None] * (dy - yh * (dy * yh).sum(-1, keepdim=True))).to(out_dtype)
 
@@ -281,6 +296,49 @@ def masked_sum_norm(embs, weights, biases, codes, missing_index, gamma, beta, ep
     return torch.nn.functional.layer_norm(tot, (tot.shape[1],), gamma, beta, eps)
 
 
+# ------------------------------------------------------------------ bf16-mode entry points (product path)
+def attention_fwd(qkv, lay, H, *, causal=False, key_mask=None, mask_rows=None, mask_div=1, out=None):
+    assert qkv.dtype == BF16
+    with torch.no_grad():
+        o, lse = _attn_core(qkv.float(), lay, H, causal, key_mask, mask_rows, mask_div)
+    if out is None:
+        return o.to(BF16), lse
+    out.copy_(o.to(BF16))
+    return out, lse
+
+
+def attention_bwd(qkv, out, lse, d_out, lay, H, q_scale, *, causal=False, key_mask=None, mask_rows=None, mask_div=1,
+                  dqkv_out=None, want_colsum=True):
+    assert d_out.dtype == BF16 and d_out.stride(0) == out.stride(0)
+    g = attention_f32_bwd(qkv.float(), out.float(), lse, d_out.float(), lay, H, q_scale, causal=causal,
+                          key_mask=key_mask, mask_rows=mask_rows, mask_div=mask_div).to(BF16)
+    if dqkv_out is not None:
+        assert dqkv_out.stride(0) == qkv.stride(0)
+        dqkv_out.copy_(g)
+        g = dqkv_out
+    return g, (g.float().sum(0) if want_colsum else None)
+
+
+def cast_bf16(src, out=None, cols_dst=None):
+    rows, cols = src.shape
+    cols_dst = cols if cols_dst is None else cols_dst
+    if out is None:
+        out = torch.zeros((rows, cols_dst), dtype=BF16)
+    out[:, :cols] = src.to(BF16)
+    out[:, cols:cols_dst] = 0
+    return out
+
+
+def colsum(x):
+    return x.float().sum(0)
+
+
+def patchify(pixels, ps, Kpad, T=1, sample_index=None, n_samples=None):
+    return patchify_f32(pixels, ps, Kpad, T, sample_index, n_samples).to(BF16)
+
+
+BF16_MODE_OPS = ["attention_fwd", "attention_bwd", "cast_bf16", "colsum", "patchify"]
+
 EMULATED_OPS = ["gemm", "expand6", "attention_f32_fwd", "attention_f32_bwd", "layernorm_fwd", "layernorm_bwd",
                 "gelu_f32_fwd", "gelu_f32_bwd", "colsum_grouped", "copy_f32", "patchify_f32", "cls_rows", "embed_bwd",
                 "frame_mean", "frame_mean_bwd", "l2norm_scale_fwd", "l2norm_scale_bwd", "text_embed_fwd",
@@ -288,23 +346,32 @@ EMULATED_OPS = ["gemm", "expand6", "attention_f32_fwd", "attention_f32_bwd", "la
 
 
 @contextlib.contextmanager
-def emulated_fp32_mode():
+def emulated_fp32_mode(precision="fp32", wide_bf16=False):
     """Patch missm_b200.ops (+ the fused `sum` head and the CUDA-only guards) with the stand-ins above and switch
-    the host side to the fp32 verification mode.  ops.gemm_f32 / colsum_f32 stay the REAL host code."""
+    the host side to the fp32 verification mode.  ops.gemm_f32 / colsum_f32 stay the REAL host code.
+    precision="bf16" exercises the PRODUCT blocks of autograd.py instead; with wide_bf16 every "bf16" buffer is
+    really fp32 (the dtype constant is swapped), which isolates the host algebra -- operand views, pitches,
+    gradient formulas -- from bf16 rounding."""
     from missm_b200 import autograd as ag, bank, fusion_ops, ops, towers
     here = globals()
-    saved = {n: getattr(ops, n) for n in EMULATED_OPS}
+    global BF16
+    names = EMULATED_OPS + (BF16_MODE_OPS if precision == "bf16" else [])
+    saved = {n: getattr(ops, n) for n in names}
+    saved_dt = (BF16, ag.BF16, ops.BF16)
+    if wide_bf16:
+        BF16 = ag.BF16 = ops.BF16 = torch.float32
     saved_guard, saved_bank_guard, saved_fusion = towers._require_cuda, bank._require_cuda_index, fusion_ops.masked_sum_norm
-    for n in EMULATED_OPS:
+    for n in names:
         setattr(ops, n, here[n])
     towers._require_cuda = lambda t, what: None
     bank._require_cuda_index = lambda mi, mdev: mi
     fusion_ops.masked_sum_norm = masked_sum_norm
-    old = ag.set_precision("fp32")
+    old = ag.set_precision(precision)
     try:
         yield
     finally:
         ag.set_precision(old)
+        BF16, ag.BF16, ops.BF16 = saved_dt
         for n, f in saved.items():
             setattr(ops, n, f)
         towers._require_cuda, bank._require_cuda_index, fusion_ops.masked_sum_norm = saved_guard, saved_bank_guard, saved_fusion
