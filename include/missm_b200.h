@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define MISSM_ABI_VERSION 4   /* 3: missm_set_persistent_sms; 4: fp32 verification mode */
+#define MISSM_ABI_VERSION 5   /* 3: missm_set_persistent_sms; 4: fp32 verification mode; 5: missm_adam_multi */
 
 int missm_version(void);
 const char* missm_last_error(void);
@@ -245,6 +245,38 @@ int missm_gelu_f32_fwd(const float* u, float* a, int64_t n, void* stream);
 int missm_gelu_f32_bwd(const float* d_a, const float* u, float* d_u, int64_t n, void* stream);
 int missm_attention_f32_fwd(const missm_attn_args* args, void* stream);
 int missm_attention_f32_bwd(const missm_attn_args* args, void* stream);
+
+/* ---------------------------------------------------------------------------------------
+ * Multi-tensor Adam (csrc/optim.cu) -- replaces torch.optim.Adam.step() as the reference drives it
+ * (train_ddp.py:205 `optim.Adam(model.parameters(), lr, weight_decay)`, :254 `optimizer.step()`): L2 weight decay
+ * folded into the gradient, no amsgrad, per-tensor step counts.  ONE launch updates every tensor of a parameter
+ * group.  All table pointers are DEVICE arrays of n_tensors (chunk_*: n_chunks) entries built by the caller:
+ * tensor t is cut into chunks of chunk_elems elements, chunk c covers elements
+ * [chunk_offset[c], chunk_offset[c] + chunk_elems) of tensor chunk_tensor[c].  grads[t] == NULL skips tensor t
+ * (torch skips parameters without a gradient).  step_size[t] = lr / (1 - beta1^step_t), bc2_sqrt[t] =
+ * sqrt(1 - beta2^step_t), computed by the caller in double.  bf16_out (may be NULL, entries may be NULL): also
+ * write the bf16 GEMM-operand copy of the updated parameter.  zero_grads: also zero the gradients
+ * (zero_grad(set_to_none=False) fused).  Everything fp32, contiguous; p / g / m / v 16-byte aligned tensors take
+ * the 128-bit path.  HBM-bound: 28 B per element (+2 bf16_out, +4 zero_grads).
+ * ------------------------------------------------------------------------------------- */
+typedef struct missm_adam_args {
+  void* const* params;
+  void* const* grads;
+  void* const* exp_avg;
+  void* const* exp_avg_sq;
+  void* const* bf16_out;
+  const int64_t* numel;
+  const float* step_size;
+  const float* bc2_sqrt;
+  const int32_t* chunk_tensor;
+  const int64_t* chunk_offset;
+  int64_t chunk_elems;
+  int32_t n_tensors, n_chunks;
+  double beta1, beta2;
+  float eps, weight_decay;
+  int32_t zero_grads;
+} missm_adam_args;
+int missm_adam_multi(const missm_adam_args* args, void* stream);
 
 #ifdef __cplusplus
 }

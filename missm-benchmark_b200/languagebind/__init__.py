@@ -12,3 +12,11 @@ from missm_b200.io_boundary import (transform_dict, LanguageBindImageTokenizer, 
                                     LanguageBindThermalTokenizer, LanguageBindImageProcessor,
                                     LanguageBindVideoProcessor, LanguageBindDepthProcessor,
                                     LanguageBindAudioProcessor, LanguageBindThermalProcessor)
+
+# MISSM_FUSED_ADAM=1: the unchanged train_ddp.py:205 (`optim.Adam(model.parameters(), ...)`) then builds the
+# one-launch multi-tensor Adam of missm_b200/optim.py.  Opt-in: rebinding a torch
+# name is not something an import should do silently.
+import os as _os
+if _os.environ.get("MISSM_FUSED_ADAM", "0") == "1":
+    from missm_b200 import optim as _optim
+    _optim.install()

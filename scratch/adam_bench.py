@@ -1,0 +1,44 @@
+"""HBM roofline check of the multi-tensor Adam (csrc/optim.cu): image-tower-sized parameter set (303 M fp32
+parameters in the tower's own tensor shapes), CUDA events around K steps, algorithmic 28 B / parameter."""
+import json
+import os
+import sys
+import time
+
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.join(ROOT, "missm-benchmark_b200"))
+from missm_b200 import optim  # noqa: E402
+
+D, F, L = 1024, 4096, 24
+shapes = []
+for _ in range(L):
+    shapes += [(D, D)] * 4 + [(D,)] * 4 + [(F, D), (F,), (D, F), (D,)] + [(D,)] * 4
+shapes += [(D, 3, 14, 14), (257, D), (D,), (768, D)]
+params = [torch.nn.Parameter(torch.randn(s, device="cuda") * 0.02) for s in shapes]
+n = sum(p.numel() for p in params)
+for p in params:
+    p.grad = torch.randn_like(p)
+res = {"params": n, "tensors": len(params)}
+for name, cls in (("fused", optim.FusedAdam), ("torch_foreach", torch.optim.Adam)):
+    opt = cls(params, lr=1e-4)
+    for _ in range(3):
+        opt.step()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t0 = time.perf_counter()
+    e0.record()
+    K = 10
+    for _ in range(K):
+        opt.step()
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / K
+    res[name] = {"ms_per_step": ms, "host_ms_per_step": (time.perf_counter() - t0) * 1e3 / K,
+                 "algorithmic_GBps": 28.0 * n / ms / 1e6}
+    del opt
+peaks = os.path.join(ROOT, "MEASURED_PEAKS.json")
+if os.path.exists(peaks):
+    res["measured_peaks"] = json.load(open(peaks))
+print(json.dumps(res))
