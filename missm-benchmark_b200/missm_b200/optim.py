@@ -80,23 +80,87 @@ class FusedAdam(torch.optim.Optimizer):
             st['exp_avg_sq'] = torch.zeros_like(p, memory_format=torch.preserve_format)
         return st
 
-    def _table(self, gi, plist):
-        """Static part of a group's table (parameter / moment pointers, sizes, chunk list), rebuilt only when a
-        tensor was re-allocated (load_state_dict, .to())."""
-        key = tuple((p.data_ptr(), self.state[p]['exp_avg'].data_ptr(), self.state[p]['exp_avg_sq'].data_ptr(),
-                     p.numel()) for p in plist)
+    def load_state_dict(self, state_dict):
+        super().load_state_dict(state_dict)
+        self._tables.clear()               # the moments were re-allocated
+
+    def _table(self, gi, group):
+        """Static part of a group's table (parameter / moment pointers, sizes, chunk list), validated and built
+        once; rebuilt when a parameter was re-allocated (`.to()`), the trainable set changed, or a state dict was
+        loaded.  The per-step host work is then one pass over the gradients."""
+        plist = [p for p in group['params'] if p.requires_grad or p.grad is not None]
+        ptrs = [p.data_ptr() for p in plist]
         hit = self._tables.get(gi)
-        if hit is not None and hit['key'] == key:
+        if hit is not None and hit['ptrs'] == ptrs:
             return hit
+        if not plist:
+            return None
+        for p in plist:
+            if not p.is_cuda or p.dtype != torch.float32 or not p.is_contiguous():
+                raise RuntimeError("missm_b200.optim.FusedAdam: parameters must be contiguous fp32 CUDA tensors "
+                                   f"(got {p.dtype} on {p.device}); there is no CPU fallback")
+        states = [self._init_state(p) for p in plist]
         dev = plist[0].device
         i64 = lambda v: torch.tensor(v, dtype=torch.int64).to(dev)
         tensor_of, offset_of = chunk_table([p.numel() for p in plist])
-        tab = dict(key=key, dev=dev, n=len(plist), n_chunks=len(tensor_of),
-                   params=i64([k[0] for k in key]), exp_avg=i64([k[1] for k in key]),
-                   exp_avg_sq=i64([k[2] for k in key]), numel=i64([k[3] for k in key]),
+        tab = dict(ptrs=ptrs, plist=plist, dev=dev, n=len(plist), n_chunks=len(tensor_of),
+                   steps=[float(st['step']) for st in states], step_tensors=[st['step'] for st in states],
+                   params=i64(ptrs), exp_avg=i64([st['exp_avg'].data_ptr() for st in states]),
+                   exp_avg_sq=i64([st['exp_avg_sq'].data_ptr() for st in states]),
+                   numel=i64([p.numel() for p in plist]),
                    chunk_tensor=torch.tensor(tensor_of, dtype=torch.int32).to(dev), chunk_offset=i64(offset_of))
         self._tables[gi] = tab
         return tab
+
+    def _prepare(self, gi, group):
+        """Host side of one step of one group -> (AdamArgs, tensors to keep alive until the launch) or None."""
+        tab = self._table(gi, group)
+        if tab is None:
+            return None
+        plist, steps = tab['plist'], tab['steps']
+        beta1, beta2 = group['betas']
+        lr = float(group['lr'])
+        gptr, ssz, bc2, keep, scal, stepped = [], [], [], [], {}, []
+        for i, p in enumerate(plist):
+            g = p.grad
+            if g is None:                          # torch skips it: no update, its step count does not advance
+                gptr.append(0), ssz.append(0.0), bc2.append(1.0)
+                continue
+            if g.dtype != torch.float32 or g.device != p.device or g.is_sparse:
+                raise RuntimeError("FusedAdam: gradients must be dense fp32 tensors on the parameter's device")
+            if not g.is_contiguous():
+                g = g.contiguous()
+                keep.append(g)
+            k = steps[i] = steps[i] + 1.0
+            sc = scal.get(k)
+            if sc is None:                         # almost always ONE distinct step count per group
+                sc = scal[k] = step_scalars(k, lr, beta1, beta2)
+            gptr.append(g.data_ptr()), ssz.append(sc[0]), bc2.append(sc[1])
+            stepped.append(tab['step_tensors'][i])
+        if not stepped:
+            return None
+        torch._foreach_add_(stepped, 1.0)          # the state's own `step` tensors (CPU scalars), one call
+        dev = tab['dev']
+        # pageable sources: the driver stages them before returning, so the host lists may die right away
+        d_g = torch.tensor(gptr, dtype=torch.int64).to(dev, non_blocking=True)
+        d_sb = torch.tensor(ssz + bc2, dtype=torch.float32).to(dev, non_blocking=True)
+        a = AdamArgs()
+        a.params, a.grads = tab['params'].data_ptr(), d_g.data_ptr()
+        a.exp_avg, a.exp_avg_sq = tab['exp_avg'].data_ptr(), tab['exp_avg_sq'].data_ptr()
+        a.bf16_out = None
+        a.numel, a.step_size, a.bc2_sqrt = tab['numel'].data_ptr(), d_sb.data_ptr(), d_sb.data_ptr() + 4 * tab['n']
+        a.chunk_tensor, a.chunk_offset = tab['chunk_tensor'].data_ptr(), tab['chunk_offset'].data_ptr()
+        a.chunk_elems, a.n_tensors, a.n_chunks = CHUNK_ELEMS, tab['n'], tab['n_chunks']
+        a.beta1, a.beta2, a.eps, a.weight_decay = beta1, beta2, group['eps'], group['weight_decay']
+        a.zero_grads = 0
+        keep += [d_g, d_sb]
+        return a, keep, tab
+
+    def _launch(self, a, tab):
+        with torch.cuda.device(tab['dev']):
+            check(lib().missm_adam_multi(ctypes.byref(a), stream_ptr()), "adam_multi")
+        ops.LAUNCHES[0] += 1
+        self.launches += 1
 
     # -------------------------------------------------------------------------------------- step
     @torch.no_grad()
@@ -106,60 +170,15 @@ class FusedAdam(torch.optim.Optimizer):
             with torch.enable_grad():
                 loss = closure()
         for gi, group in enumerate(self.param_groups):
-            plist = [p for p in group['params'] if p.requires_grad or p.grad is not None]
-            if not plist:
+            prep = self._prepare(gi, group)
+            if prep is None:
                 continue
-            for p in plist:
-                if not p.is_cuda or p.dtype != torch.float32 or not p.is_contiguous():
-                    raise RuntimeError("missm_b200.optim.FusedAdam: parameters must be contiguous fp32 CUDA tensors "
-                                       f"(got {p.dtype} on {p.device}); there is no CPU fallback")
-                self._init_state(p)
-            beta1, beta2 = group['betas']
-            lr = float(group['lr'])
-            tab = self._table(gi, plist)
-            gptr, ssz, bc2, keep, scal = [], [], [], [], {}
-            for p in plist:
-                g = p.grad
-                st = self.state[p]
-                if g is None:
-                    gptr.append(0), ssz.append(0.0), bc2.append(1.0)
-                    continue
-                if g.is_sparse:
-                    raise RuntimeError("Adam does not support sparse gradients")
-                if g.dtype != torch.float32 or g.device != p.device:
-                    raise RuntimeError("FusedAdam: gradients must be fp32 tensors on the parameter's device")
-                if not g.is_contiguous():
-                    g = g.contiguous()
-                    keep.append(g)
-                st['step'] += 1
-                k = st['step'].item()
-                if k not in scal:                  # almost always ONE distinct step count per group
-                    scal[k] = step_scalars(k, lr, beta1, beta2)
-                gptr.append(g.data_ptr()), ssz.append(scal[k][0]), bc2.append(scal[k][1])
-            if not any(gptr):
-                continue
-            dev = tab['dev']
-            # pageable sources: the driver stages them before returning, so the host lists may die right away
-            d_g = torch.tensor(gptr, dtype=torch.int64).to(dev, non_blocking=True)
-            d_s = torch.tensor(ssz, dtype=torch.float32).to(dev, non_blocking=True)
-            d_b = torch.tensor(bc2, dtype=torch.float32).to(dev, non_blocking=True)
-            a = AdamArgs()
-            a.params, a.grads = tab['params'].data_ptr(), d_g.data_ptr()
-            a.exp_avg, a.exp_avg_sq = tab['exp_avg'].data_ptr(), tab['exp_avg_sq'].data_ptr()
-            a.bf16_out = None
-            a.numel, a.step_size, a.bc2_sqrt = tab['numel'].data_ptr(), d_s.data_ptr(), d_b.data_ptr()
-            a.chunk_tensor, a.chunk_offset = tab['chunk_tensor'].data_ptr(), tab['chunk_offset'].data_ptr()
-            a.chunk_elems, a.n_tensors, a.n_chunks = CHUNK_ELEMS, tab['n'], tab['n_chunks']
-            a.beta1, a.beta2, a.eps, a.weight_decay = beta1, beta2, group['eps'], group['weight_decay']
-            a.zero_grads = 0
-            with torch.cuda.device(dev):
-                check(lib().missm_adam_multi(ctypes.byref(a), stream_ptr()), "adam_multi")
-            ops.LAUNCHES[0] += 1
-            self.launches += 1
+            a, keep, tab = prep
+            self._launch(a, tab)
             # the kernel wrote through raw pointers: advance the parameters' version counters (host-only, no launch)
             # so that everything keyed on them -- the cached bf16 GEMM-operand copies of autograd.cached_weight,
             # autograd's saved-tensor checks -- sees the update exactly as after an in-place torch op
-            touched = tuple(p for p in plist if p.grad is not None)
+            touched = tuple(p for p in tab['plist'] if p.grad is not None)
             torch._C._autograd._unsafe_set_version_counter(touched, tuple(p._version + 1 for p in touched))
         return loss
 

@@ -2,6 +2,7 @@
 as the reference drives it (train_ddp.py:205,254): same parameters, moments and trajectories to fp32 rounding,
 state dicts interchangeable, the fused bf16 operand copy / zero_grad outputs of the ABI, and -- through the whole
 CUDA path -- that the bf16 GEMM-operand caches follow an update made through raw pointers."""
+import copy
 import ctypes
 import os
 import sys
@@ -67,7 +68,8 @@ def test_state_dict_interchange():
             p.grad = gr.clone()
         oa.step()
     ob = optim.FusedAdam(pb, lr=1e-3)
-    ob.load_state_dict(oa.state_dict())                # resume a torch.optim.Adam run
+    # (state_dict() hands out the live state tensors: a real resume goes through torch.save / torch.load)
+    ob.load_state_dict(copy.deepcopy(oa.state_dict()))   # resume a torch.optim.Adam run
     with torch.no_grad():
         for a, b in zip(pa, pb):
             b.copy_(a)
@@ -77,7 +79,7 @@ def test_state_dict_interchange():
         oa.step(), ob.step()
     assert max(relmax(b, a) for a, b in zip(pa, pb)) < 2e-6
     oa2 = torch.optim.Adam(pa, lr=1e-3)
-    oa2.load_state_dict(ob.state_dict())               # and back
+    oa2.load_state_dict(copy.deepcopy(ob.state_dict()))   # and back
     assert float(oa2.state[pa[0]]['step']) == 4.0
 
 
