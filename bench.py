@@ -42,14 +42,21 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--layers", type=int, default=24, help=argparse.SUPPRESS)  # debugging only
+    # variants beyond the headline workload; the defaults ARE the headline
+    ap.add_argument("--lora-r", type=int, default=0, help="peft-style LoRA rank on the towers' attention projections "
+                    "(reference config default 2; encoder frozen, adapters trained)")
+    ap.add_argument("--optimizer", default="none", choices=["none", "fused", "torch"],
+                    help="also time optimizer.step(): missm_b200.optim.FusedAdam or torch.optim.Adam")
     return ap.parse_args()
 
 
-def full_configs(layers=24):
+def full_configs(layers=24, lora_r=0):
     import restatement as R
     from missm_b200 import config as C
     v = {k: val for k, val in C.VIT_L14.items() if k != 'lora_r'}
     v['num_hidden_layers'] = layers
+    if lora_r:
+        v['lora_r'], v['lora_alpha'] = lora_r, 16
     t = dict(C.CLIP_TEXT)
     cfgs = {m: R.vision_config(**v) for m in MODALS}
     return cfgs, R.text_config(**t)
@@ -188,7 +195,7 @@ def run_gpu_arm(a):
         dist.init_process_group("nccl", device_id=dev)
     ops.lib()
 
-    cfgs, tcfg = full_configs(a.layers)
+    cfgs, tcfg = full_configs(a.layers, a.lora_r)
     model = shapes.build_finetune(cfgs, tcfg, MODALS, 'sum', 3, 768, 256, dropout_prob=0.1)
     sd = R.synth_state_dict([(k, tuple(v.shape)) for k, v in model.state_dict().items()])
     shapes.load_named(model, sd)
@@ -218,10 +225,19 @@ def run_gpu_arm(a):
     n_missing = int((mi_host != 0).sum())
     present_sample_towers = len(MODALS) * B - n_missing
 
+    opt = None
+    if a.optimizer != "none":
+        from missm_b200 import optim as moptim
+        trainable = [p for p in model.parameters() if p.requires_grad]
+        # the call of train_ddp.py:205 (lr 1e-4, weight_decay 0 are the script's defaults, :40-41)
+        opt = (moptim.FusedAdam if a.optimizer == "fused" else torch.optim.Adam)(trainable, lr=1e-4, weight_decay=0)
+
     def step_resident():
         net.zero_grad(set_to_none=True)
         loss = crit(net(data, mi), labels)
         loss.backward()
+        if opt is not None:
+            opt.step()
         return loss
 
     def step_e2e():
@@ -231,6 +247,8 @@ def run_gpu_arm(a):
         l_ = labels_host.to(dev, non_blocking=True)
         loss = crit(net(host, mi_host), l_)
         loss.backward()
+        if opt is not None:
+            opt.step()
         return float(loss.detach())                            # device -> host read of the step's result
 
     def barrier():
@@ -311,7 +329,15 @@ def run_gpu_arm(a):
                     "sample": f"{n} samples x 3 full-size towers fwd+bwd, fp32, oracle/restatement.py, 1 warm-up + 1 timed"}
 
     if rank == 0:
-        algo_tf = present_sample_towers * 3 * 162.0e9 * world * a.steps / (ms / 1e3) / 1e12
+        # fwd+bwd = 3 x forward flops; with a frozen (LoRA) encoder the weight gradients are not computed: 2 x
+        flop_factor = 2.0 if a.lora_r else 3.0
+        algo_tf = present_sample_towers * flop_factor * 162.0e9 * world * a.steps / (ms / 1e3) / 1e12
+        variant = []
+        if a.lora_r:
+            variant.append(f"LoRA r={a.lora_r} on q/k/v/out_proj, encoder frozen (dgrad-only backward, flops counted as 2 x forward)")
+        if opt is not None:
+            variant.append(f"optimizer.step() inside the timed step: {type(opt).__module__}.{type(opt).__name__}, "
+                           f"{sum(p.numel() for p in model.parameters() if p.requires_grad) / 1e6:.1f} M trainable parameters")
         line = {
             "metric": METRIC, "value": samples_per_s, "unit": "samples/s", "n_gpus": world, "steps": a.steps,
             "warmup": max(a.warmup, 3), "ms_per_step": ms / a.steps, "higher_is_better": True, "scaling": "weak",
@@ -321,7 +347,9 @@ def run_gpu_arm(a):
                        "ddp": (None if world == 1 else "DistributedDataParallel as train_ddp.py:189" +
                                (" + gradient_as_bucket_view (measurement switch)" if os.environ.get("MISSM_BENCH_BUCKET_VIEW") else "")),
                        "host_issue_ms_per_step": host_issue_ms,
-                       "step": "zero_grad + forward + CrossEntropy + backward (DDP allreduce at N>1); optimizer excluded (metric is fwd+bwd)",
+                       "variant": "; ".join(variant) if variant else None,
+                       "step": "zero_grad + forward + CrossEntropy + backward (DDP allreduce at N>1); " +
+                               ("optimizer excluded (metric is fwd+bwd)" if opt is None else "optimizer.step() included"),
                        "l2": "working set >> 126 MB L2 every step (1.8 GB bf16 weights + >30 GB activations)",
                        "encoder_tflops_algorithmic": algo_tf,
                        "encoder_frac_of_bf16_peak": algo_tf / world / pk["bf16_tflops"], "peaks": pk_src},

@@ -8,6 +8,7 @@ DDP at train_ddp.py:189 runs with find_unused_parameters=False.
 import os
 
 import torch
+from torch.utils.weak import WeakIdKeyDictionary
 
 from . import ops
 from .ops import BF16, F32, EPI_DGELU, EPI_GELU, EPI_PATCH, EPI_RESID
@@ -72,13 +73,17 @@ def _contig(g):
 # ------------------------------------------------------------------------------------------
 # bf16 operand copies of fp32 master weights, cached on the owning module by parameter version
 # ------------------------------------------------------------------------------------------
+def _versions(params):
+    return tuple((p._version, p.data_ptr()) for p in params)
+
+
 def cached_weight(cache, name, params, build):
-    ver = tuple((p._version, p.data_ptr()) for p in params)
+    ver = _versions(params)
     hit = cache.get(name)
     if hit is not None and hit[0] == ver:
         return hit[1]
     val = build()
-    cache[name] = (ver, val)
+    cache[name] = (ver, val, tuple(params))
     return val
 
 
@@ -86,20 +91,83 @@ def _w2d(p):
     return p.detach().reshape(p.shape[0], -1)
 
 
+# parameter -> (cache dict, entry name, slot) of the bf16 GEMM-operand copy made from it, for optimizers that can
+# write that copy themselves while they update the parameter (optim.FusedAdam: `bf16_out` of missm_adam_multi)
+_SINKS = WeakIdKeyDictionary()         # keyed by identity: Tensor.__eq__ is elementwise
+
+
 def bf16_weight(cache, name, p, cols_dst=None):
-    return cached_weight(cache, name, (p,), lambda: ops.cast_bf16(_w2d(p), cols_dst=cols_dst))
+    val = cached_weight(cache, name, (p,), lambda: ops.cast_bf16(_w2d(p), cols_dst=cols_dst))
+    if cols_dst is None:
+        _SINKS[p] = (cache, name, None)
+    return val
 
 
 def packed_qkv(cache, qw, kw, vw, qb, kb, vb):
-    def build():
-        D = qw.shape[0]
+    D = qw.shape[0]
+
+    def build_w():
         w = torch.empty((3 * D, qw.shape[1]), device=qw.device, dtype=BF16)
-        b = torch.empty((3 * D,), device=qw.device, dtype=F32)
-        for i, (wi, bi) in enumerate(((qw, qb), (kw, kb), (vw, vb))):
+        for i, wi in enumerate((qw, kw, vw)):
             ops.cast_bf16(wi.detach(), out=w[i * D:(i + 1) * D])
+        return w
+
+    def build_b():
+        b = torch.empty((3 * D,), device=qw.device, dtype=F32)
+        for i, bi in enumerate((qb, kb, vb)):
             ops.copy_f32(bi.detach(), b[i * D:(i + 1) * D])
-        return w, b
-    return cached_weight(cache, "qkv", (qw, kw, vw, qb, kb, vb), build)
+        return b
+
+    w = cached_weight(cache, "qkv_w", (qw, kw, vw), build_w)
+    b = cached_weight(cache, "qkv_b", (qb, kb, vb), build_b)
+    for i, wi in enumerate((qw, kw, vw)):
+        _SINKS[wi] = (cache, "qkv_w", i)
+    return w, b
+
+
+def plan_operand_refresh(touched):
+    """For an optimizer about to update the parameters `touched` through raw pointers: which of them have a bf16
+    operand copy it may rewrite in the same pass.  -> ({id(param): bf16 destination tensor}, entries to `restamp`
+    after the update).  An entry qualifies only if it is FRESH now and every parameter it was built from is either
+    untouched or has this entry as its sink -- then rewriting the touched slices keeps it exact; anything else is
+    left alone and rebuilds itself at the next forward through the ordinary version check."""
+    touched_ids = {id(p) for p in touched}
+    by_entry = {}
+    for p in touched:
+        sink = _SINKS.get(p)
+        if sink is not None:
+            by_entry.setdefault((id(sink[0]), sink[1]), (sink[0], sink[1], []))[2].append((p, sink[2]))
+    dst, entries = {}, []
+    for cache, name, plist in by_entry.values():
+        hit = cache.get(name)
+        if hit is None or hit[0] != _versions(hit[2]):
+            continue                                           # absent or already stale
+        mine = {id(p) for p, _ in plist}
+        if any(id(q) in touched_ids and id(q) not in mine for q in hit[2]):
+            continue
+        for p, slot in plist:
+            val = hit[1]
+            if slot is not None:
+                rows = p.shape[0]
+                val = val[slot * rows:(slot + 1) * rows]
+            if val.numel() != p.numel() or not val.is_contiguous():
+                break
+            dst[id(p)] = val
+        else:
+            entries.append((cache, name))
+            continue
+        for p, _ in plist:                                     # a slice did not line up: drop the whole entry
+            dst.pop(id(p), None)
+    return dst, entries
+
+
+def restamp(entries):
+    """Mark the entries of plan_operand_refresh current again (their parameters' versions have advanced and the
+    optimizer rewrote their bf16 slices from the updated values)."""
+    for cache, name in entries:
+        hit = cache.get(name)
+        if hit is not None:
+            cache[name] = (_versions(hit[2]), hit[1], hit[2])
 
 
 class AttnMeta:

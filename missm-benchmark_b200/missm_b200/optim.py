@@ -13,10 +13,12 @@ touch `param_groups[i]['lr']`.  No CPU fallback: parameters must be fp32 CUDA te
 """
 import ctypes
 import math
+import os
 
 import torch
 
 from ._lib import check, lib, stream_ptr
+from . import autograd as ag
 from . import ops
 
 CHUNK_ELEMS = 32768
@@ -70,6 +72,7 @@ class FusedAdam(torch.optim.Optimizer):
         super().__init__(params, defaults)
         self._tables = {}
         self.launches = 0
+        self.refresh_operands = os.environ.get("MISSM_ADAM_REFRESH", "1") != "0"
 
     # ------------------------------------------------------------------------------ device tables
     def _init_state(self, p):
@@ -120,7 +123,7 @@ class FusedAdam(torch.optim.Optimizer):
         plist, steps = tab['plist'], tab['steps']
         beta1, beta2 = group['betas']
         lr = float(group['lr'])
-        gptr, ssz, bc2, keep, scal, stepped = [], [], [], [], {}, []
+        gptr, ssz, bc2, keep, scal, stepped, touched = [], [], [], [], {}, [], []
         for i, p in enumerate(plist):
             g = p.grad
             if g is None:                          # torch skips it: no update, its step count does not advance
@@ -137,6 +140,7 @@ class FusedAdam(torch.optim.Optimizer):
                 sc = scal[k] = step_scalars(k, lr, beta1, beta2)
             gptr.append(g.data_ptr()), ssz.append(sc[0]), bc2.append(sc[1])
             stepped.append(tab['step_tensors'][i])
+            touched.append(p)
         if not stepped:
             return None
         torch._foreach_add_(stepped, 1.0)          # the state's own `step` tensors (CPU scalars), one call
@@ -147,13 +151,23 @@ class FusedAdam(torch.optim.Optimizer):
         a = AdamArgs()
         a.params, a.grads = tab['params'].data_ptr(), d_g.data_ptr()
         a.exp_avg, a.exp_avg_sq = tab['exp_avg'].data_ptr(), tab['exp_avg_sq'].data_ptr()
-        a.bf16_out = None
+        # bf16 GEMM-operand copies the forward path keeps of these parameters: rewritten by the same pass
+        # (saves the 6 B / element cast kernels of the next forward); anything not eligible rebuilds itself
+        a.bf16_out, entries = None, []
+        if self.refresh_operands:
+            dst, entries = ag.plan_operand_refresh(touched)
+            if dst:
+                d_w = torch.tensor([dst[id(p)].data_ptr() if id(p) in dst else 0 for p in plist],
+                                   dtype=torch.int64).to(dev, non_blocking=True)
+                a.bf16_out = d_w.data_ptr()
+                keep.append(d_w)
         a.numel, a.step_size, a.bc2_sqrt = tab['numel'].data_ptr(), d_sb.data_ptr(), d_sb.data_ptr() + 4 * tab['n']
         a.chunk_tensor, a.chunk_offset = tab['chunk_tensor'].data_ptr(), tab['chunk_offset'].data_ptr()
         a.chunk_elems, a.n_tensors, a.n_chunks = CHUNK_ELEMS, tab['n'], tab['n_chunks']
         a.beta1, a.beta2, a.eps, a.weight_decay = beta1, beta2, group['eps'], group['weight_decay']
         a.zero_grads = 0
         keep += [d_g, d_sb]
+        tab['touched'], tab['entries'] = touched, entries
         return a, keep, tab
 
     def _launch(self, a, tab):
@@ -178,8 +192,9 @@ class FusedAdam(torch.optim.Optimizer):
             # the kernel wrote through raw pointers: advance the parameters' version counters (host-only, no launch)
             # so that everything keyed on them -- the cached bf16 GEMM-operand copies of autograd.cached_weight,
             # autograd's saved-tensor checks -- sees the update exactly as after an in-place torch op
-            touched = tuple(p for p in tab['plist'] if p.grad is not None)
+            touched = tuple(tab['touched'])
             torch._C._autograd._unsafe_set_version_counter(touched, tuple(p._version + 1 for p in touched))
+            ag.restamp(tab['entries'])
         return loss
 
 

@@ -3,9 +3,13 @@ train_ddp.py:205,221,254): constructor contract of torch.optim.Adam, chunk table
 layout, the opt-in rebinding of torch.optim.Adam, and the loud failure without a CUDA device.  The kernel itself
 (csrc/optim.cu) is checked against torch.optim.Adam on the B200 by tests/test_optim_gpu.py."""
 import math
+import os
+import sys
 
 import pytest
 import torch
+
+sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
 
 
 def test_chunk_table_covers_every_element_once():
@@ -65,3 +69,41 @@ def test_install_rebinds_and_restores():
     finally:
         optim.uninstall()
     assert torch.optim.Adam is orig
+
+
+def test_operand_refresh_plan_only_touches_exact_entries():
+    """autograd.plan_operand_refresh / restamp: which cached bf16 operand copies an optimizer may rewrite itself."""
+    import ops_emulation as E
+    from missm_b200 import autograd as ag
+    D = 16
+    mk = lambda *s: torch.nn.Parameter(torch.randn(*s))
+    qw, kw, vw, ow = mk(D, D), mk(D, D), mk(D, D), mk(D, D)
+    qb, kb, vb = mk(D), mk(D), mk(D)
+    patch = mk(D, 3, 2, 2)
+    cache = {}
+    with E.emulated_fp32_mode(precision="bf16"):
+        w, b = ag.packed_qkv(cache, qw, kw, vw, qb, kb, vb)
+        wo = ag.bf16_weight(cache, "o", ow)
+        ag.bf16_weight(cache, "patch", patch, cols_dst=16)          # padded layout: never a sink
+        # everything fresh, all weights touched: q/k/v slices of the pack + o qualify, the padded patch copy does not
+        dst, entries = ag.plan_operand_refresh([qw, kw, vw, ow, qb, patch])
+        assert set(dst) == {id(qw), id(kw), id(vw), id(ow)}
+        assert dst[id(kw)].data_ptr() == w[D:2 * D].data_ptr() and dst[id(ow)].data_ptr() == wo.data_ptr()
+        assert sorted(n for _, n in entries) == ["o", "qkv_w"]
+        # simulate the optimizer: raw-pointer update = new values + version bump, bf16 slices rewritten
+        with torch.no_grad():
+            for p_ in (qw, kw, vw, ow, qb):
+                p_.add_(1.0)
+            for p_ in (qw, kw, vw, ow):
+                dst[id(p_)].copy_(p_.detach().to(torch.bfloat16))
+        ag.restamp(entries)
+        w2, b2 = ag.packed_qkv(cache, qw, kw, vw, qb, kb, vb)
+        assert w2.data_ptr() == w.data_ptr() and torch.equal(w2[:D], qw.detach().to(torch.bfloat16))   # not rebuilt
+        assert b2.data_ptr() != b.data_ptr() and torch.equal(b2[:D], qb.detach())                      # biases rebuilt
+        # an entry that is already stale (k changed behind the cache's back) is left to rebuild itself
+        with torch.no_grad():
+            kw.mul_(2.0)
+        dst, entries = ag.plan_operand_refresh([qw, vw])
+        assert dst == {} and entries == []
+        w3, _ = ag.packed_qkv(cache, qw, kw, vw, qb, kb, vb)
+        assert torch.equal(w3[D:2 * D], kw.detach().to(torch.bfloat16))
