@@ -21,7 +21,8 @@ n = sum(p.numel() for p in params)
 for p in params:
     p.grad = torch.randn_like(p)
 res = {"params": n, "tensors": len(params)}
-for name, cls in (("fused", optim.FusedAdam), ("torch_foreach", torch.optim.Adam)):
+QUICK = "--quick" in sys.argv          # the ncu target: FusedAdam only, a few steps
+for name, cls in ((("fused", optim.FusedAdam),) if QUICK else (("fused", optim.FusedAdam), ("torch_foreach", torch.optim.Adam))):
     opt = cls(params, lr=1e-4)
     for _ in range(3):
         opt.step()
@@ -29,7 +30,7 @@ for name, cls in (("fused", optim.FusedAdam), ("torch_foreach", torch.optim.Adam
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     t0 = time.perf_counter()
     e0.record()
-    K = 10
+    K = 3 if QUICK else 10
     for _ in range(K):
         opt.step()
     e1.record()
