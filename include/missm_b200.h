@@ -24,7 +24,8 @@
 extern "C" {
 #endif
 
-#define MISSM_ABI_VERSION 5   /* 3: missm_set_persistent_sms; 4: fp32 verification mode; 5: missm_adam_multi */
+#define MISSM_ABI_VERSION 6   /* 3: missm_set_persistent_sms; 4: fp32 verification mode; 5: missm_adam_multi;
+                                 6: missm_image_preprocess */
 
 int missm_version(void);
 const char* missm_last_error(void);
@@ -277,6 +278,30 @@ typedef struct missm_adam_args {
   int32_t zero_grads;
 } missm_adam_args;
 int missm_adam_multi(const missm_adam_args* args, void* stream);
+
+/* ---------------------------------------------------------------------------------------
+ * GPU input pipeline for the image-shaped modalities (csrc/preprocess.cu) -- replaces the per-sample torchvision
+ * chain of the reference's processors: ToTensor -> Resize(S, BICUBIC) -> CenterCrop(S) -> Normalize
+ * (languagebind/image/processing_image.py:20-29, thermal/processing_thermal.py:15-25) and, for depth,
+ * DepthNorm in front of it (depth/processing_depth.py:21-57).  One launch per decoded image:
+ *   v   = clamp(src / pre_div, clip_lo, clip_hi) / post_div        (ToTensor: pre_div 255, no clip, post_div 1;
+ *                                                                   DepthNorm: 1000, [0.01, max_depth], max_depth)
+ *   r   = bicubic resample of v so that the SHORTER side becomes S (the other int(S * long / short)),
+ *         align_corners = False; antialias = 0: 4-tap cubic convolution, A = -0.75, clamped border indices
+ *         (torchvision <= 0.16 on tensors); antialias = 1: area-scaled filter, A = -0.5, support 2 * scale,
+ *         truncated + renormalised at the border (torchvision >= 0.17 default)
+ *   dst = (center S x S crop of r - mean[c]) / std[c]              fp32 [3, S, S], device
+ * src: device, uint8 [H, W, 3] (src_f32 = 0) or float [H, W] replicated to 3 channels (src_f32 = 1).
+ * ------------------------------------------------------------------------------------- */
+typedef struct missm_preproc_args {
+  const void* src;
+  float* dst;
+  int32_t src_f32, H, W, S, antialias;
+  float pre_div, clip_lo, clip_hi, post_div;
+  float mean[3];
+  float std_[3];
+} missm_preproc_args;
+int missm_image_preprocess(const missm_preproc_args* args, void* stream);
 
 #ifdef __cplusplus
 }

@@ -44,6 +44,7 @@ SIGNATURES = {
     "missm_attention_f32_fwd": [P, P],
     "missm_attention_f32_bwd": [P, P],
     "missm_adam_multi": [P, P],
+    "missm_image_preprocess": [P, P],
 }
 # exported but with non-standard return types / no args
 OTHER_EXPORTS = ["missm_version", "missm_last_error"]

@@ -378,6 +378,35 @@ def gather_rows(src, idx, n_rows):
     return dst
 
 
+# ------------------------------------------------------------------------------ input pipeline
+class PreprocArgs(ctypes.Structure):
+    """Mirror of `missm_preproc_args` (include/missm_b200.h)."""
+    _fields_ = [("src", ctypes.c_void_p), ("dst", ctypes.c_void_p),
+                ("src_f32", ctypes.c_int32), ("H", ctypes.c_int32), ("W", ctypes.c_int32), ("S", ctypes.c_int32),
+                ("antialias", ctypes.c_int32),
+                ("pre_div", ctypes.c_float), ("clip_lo", ctypes.c_float), ("clip_hi", ctypes.c_float),
+                ("post_div", ctypes.c_float), ("mean", ctypes.c_float * 3), ("std_", ctypes.c_float * 3)]
+
+
+def image_preprocess(src, out, S, mean, std, *, antialias, pre_div=255.0, clip_lo=float("-inf"),
+                     clip_hi=float("inf"), post_div=1.0):
+    """src: CUDA uint8 [H, W, 3] or float32 [H, W] (contiguous) -> out: CUDA float32 [3, S, S] (a slice of the batch
+    tensor): divide / clip / divide, bicubic resize of the shorter side to S, center crop, normalise."""
+    assert src.is_cuda and src.is_contiguous() and out.is_cuda and out.is_contiguous()
+    assert out.dtype == F32 and tuple(out.shape) == (3, S, S)
+    f32 = src.dtype == F32
+    assert (f32 and src.dim() == 2) or (src.dtype == torch.uint8 and src.dim() == 3 and src.shape[2] == 3), \
+        "expected uint8 [H, W, 3] or float32 [H, W]"
+    a = PreprocArgs()
+    a.src, a.dst, a.src_f32 = src.data_ptr(), out.data_ptr(), int(f32)
+    a.H, a.W, a.S, a.antialias = src.shape[0], src.shape[1], S, int(bool(antialias))
+    a.pre_div, a.clip_lo, a.clip_hi, a.post_div = pre_div, clip_lo, clip_hi, post_div
+    a.mean, a.std_ = (ctypes.c_float * 3)(*mean), (ctypes.c_float * 3)(*std)
+    LAUNCHES[0] += 1
+    check(lib().missm_image_preprocess(ctypes.byref(a), stream_ptr()), "image_preprocess")
+    return out
+
+
 # ------------------------------------------------------------------- fp32 verification mode
 # (MISSM_PRECISION=fp32; csrc/fp32_mode.cu)  Not a performance path: every GEMM expands both fp32 operands into
 # six bf16 pieces along the contraction dimension and runs ONE tcgen05 bf16 GEMM over K' = 6 K.

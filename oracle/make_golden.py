@@ -191,6 +191,37 @@ def lora():
           (len(out['trainable']), len(gn), sum(k.startswith('grad/') for k in out)))
 
 
+PREPROC_CASES = [('image', 11, 300, 400), ('image', 12, 517, 231), ('image', 13, 100, 180), ('thermal', 14, 224, 224),
+                 ('image', 15, 1080, 1920), ('depth', 16, 480, 640), ('depth', 17, 150, 97)]
+
+
+def preproc():
+    """the reference's OWN transforms (get_image_transform / get_thermal_transform /
+    get_depth_transform, run here with this image's torchvision) on synthetic decoded images; every 7th output pixel
+    is stored (32 x 32 x 3 per case) -- enough to pin resize geometry, crop offsets and normalisation."""
+    import numpy as np
+    import torchvision
+    from PIL import Image
+    ref_shim.install()
+    from languagebind.image.processing_image import get_image_transform
+    from languagebind.thermal.processing_thermal import get_thermal_transform
+    from languagebind.depth.processing_depth import get_depth_transform
+    import languagebind as lb
+    cfg = lb.config_dict['depth'](text_config=dict(TINY_T), vision_config=dict(TINY_V), projection_dim=64)
+    tfs = {'image': get_image_transform(cfg), 'thermal': get_thermal_transform(cfg), 'depth': get_depth_transform(cfg)}
+    out = {'meta': dict(cases=PREPROC_CASES, stride=7, torchvision=torchvision.__version__,
+                        max_depth=float(cfg.vision_config.max_depth))}
+    for kind, seed, H, W in PREPROC_CASES:
+        if kind == 'depth':
+            y = tfs[kind](R.synth_depth(seed, H, W))
+        else:
+            y = tfs[kind](Image.fromarray(R.synth_image(seed, H, W)))
+        assert tuple(y.shape) == (3, 224, 224), y.shape
+        out[f'{kind}/{seed}'] = y[:, ::7, ::7].clone()
+    torch.save(out, os.path.join(GOLD, 'preproc.pt'))
+    print('preproc golden written with torchvision', torchvision.__version__)
+
+
 def full():
     """BASELINE.json config 1: image ViT-L/14 224 + text, forward, B = 8, one image-missing
     sample, CPU fp32; plus a B = 4 fwd+bwd step (loss and gradient norms)."""
@@ -237,8 +268,12 @@ if __name__ == '__main__':
     ap = argparse.ArgumentParser()
     ap.add_argument('--full', action='store_true')
     ap.add_argument('--only-lora', action='store_true')
+    ap.add_argument('--only-preproc', action='store_true')
     a = ap.parse_args()
     os.makedirs(GOLD, exist_ok=True)
+    preproc()
+    if a.only_preproc:
+        sys.exit(0)
     lora()
     if a.only_lora:
         sys.exit(0)

@@ -317,6 +317,59 @@ def finetune_forward(sd, fusion_type, modality_types, data, missing_index, cfgs,
     return fusion_forward(sd, fusion_type, modality_types, emb, missing_index), emb
 
 
+# ------------------------------------------------------------------ input pipeline (image-shaped modalities)
+OPENAI_DATASET_MEAN = (0.48145466, 0.4578275, 0.40821073)      # languagebind/image/processing_image.py:10-11
+OPENAI_DATASET_STD = (0.26862954, 0.26130258, 0.27577711)
+
+
+def image_transform(img_u8_hwc, size=224, antialias=True):
+    """get_image_transform / get_thermal_transform (processing_image.py:20-29, thermal/processing_thermal.py:15-25):
+    ToTensor -> Resize(224, BICUBIC) -> CenterCrop(224) -> Normalize, on a decoded RGB image (numpy uint8 [H, W, 3]).
+    torchvision is the third party the reference calls (unpinned): `antialias` is its Resize default on tensors,
+    False up to 0.16 (the reference's era), True from 0.17 (what the reference computes in this image)."""
+    import numpy as np
+    from torchvision.transforms import InterpolationMode
+    from torchvision.transforms import functional as TF
+    t = torch.from_numpy(np.ascontiguousarray(img_u8_hwc)).permute(2, 0, 1).contiguous().to(torch.float32).div(255)
+    t = TF.resize(t, size, interpolation=InterpolationMode.BICUBIC, antialias=antialias)
+    t = TF.center_crop(t, size)
+    return TF.normalize(t, OPENAI_DATASET_MEAN, OPENAI_DATASET_STD)
+
+
+def depth_transform(depth_f32_hw, max_depth=10.0, size=224, antialias=True):
+    """get_depth_transform (depth/processing_depth.py:21-57): DepthNorm (/1000, clip [0.01, max_depth], / max_depth,
+    one channel repeated to three), then the image chain."""
+    import numpy as np
+    from torchvision.transforms import InterpolationMode
+    from torchvision.transforms import functional as TF
+    d = depth_f32_hw.astype(np.float32) / 1000.0
+    d = d.clip(min=0.01)
+    d = d.clip(max=max_depth)
+    d /= max_depth
+    t = torch.from_numpy(d).unsqueeze(0).repeat(3, 1, 1).to(torch.float32)
+    t = TF.resize(t, size, interpolation=InterpolationMode.BICUBIC, antialias=antialias)
+    t = TF.center_crop(t, size)
+    return TF.normalize(t, OPENAI_DATASET_MEAN, OPENAI_DATASET_STD)
+
+
+def synth_image(seed, H, W):
+    """Deterministic decoded 'photo': smooth gradients + noise, uint8 [H, W, 3] (numpy Generator, platform independent)."""
+    import numpy as np
+    rng = np.random.default_rng(seed)
+    yy, xx = np.mgrid[0:H, 0:W].astype(np.float32)
+    base = np.stack([127 + 100 * np.sin(xx / 17.0 + c) * np.cos(yy / 23.0 - c) for c in range(3)], -1)
+    return np.clip(base + rng.integers(-40, 41, (H, W, 3)), 0, 255).astype(np.uint8)
+
+
+def synth_depth(seed, H, W):
+    """Deterministic 16-bit depth map in millimetres (0 = holes, up to 12 m so that both clips act), float32 [H, W]."""
+    import numpy as np
+    rng = np.random.default_rng(seed)
+    d = rng.integers(0, 12000, (H, W)).astype(np.float32)
+    d[rng.random((H, W)) < 0.05] = 0.0
+    return d
+
+
 # ------------------------------------------------------------------ deterministic synthetic setup
 def synth_param(name, shape, std):
     """Order-independent synthetic weights: each tensor is drawn from its own generator seeded by

@@ -337,6 +337,58 @@ def patchify(pixels, ps, Kpad, T=1, sample_index=None, n_samples=None):
     return patchify_f32(pixels, ps, Kpad, T, sample_index, n_samples).to(BF16)
 
 
+# ------------------------------------------------------------------ missm_image_preprocess (csrc/preprocess.cu)
+def _cubic_aa(x):
+    a = -0.5
+    x = x.abs()
+    return torch.where(x < 1, ((a + 2) * x - (a + 3)) * x * x + 1,
+                       torch.where(x < 2, (((x - 5) * x + 8) * x - 4) * a, torch.zeros_like(x)))
+
+
+def _resample_matrix(in_size, out_size, antialias):
+    """[out_size, in_size] fp32 matrix of the header's resampling rule along one axis."""
+    m = torch.zeros((out_size, in_size), dtype=F32)
+    scale = torch.tensor(in_size, dtype=F32) / torch.tensor(out_size, dtype=F32)
+    o = torch.arange(out_size, dtype=F32)
+    if not antialias:
+        A = -0.75
+        # one rounding, as a fused multiply-add gives (aten's CPU kernel and nvcc both contract this expression)
+        src = (scale.double() * (o.double() + 0.5) - 0.5).to(F32)
+        fl = src.floor()
+        t = src - fl
+        c1 = lambda x: ((A + 2) * x - (A + 3)) * x * x + 1
+        c2 = lambda x: ((A * x - 5 * A) * x + 8 * A) * x - 4 * A
+        for j, w in enumerate((c2(t + 1), c1(t), c1(1 - t), c2(2 - t))):
+            idx = (fl.long() - 1 + j).clamp(0, in_size - 1)
+            m.index_put_((torch.arange(out_size), idx), w, accumulate=True)
+        return m
+    support = 2.0 * scale if scale >= 1 else torch.tensor(2.0)
+    invscale = 1.0 / scale if scale >= 1 else torch.tensor(1.0)
+    center = scale * (o + 0.5)
+    lo = (center - support + 0.5).to(torch.int64).clamp_min(0)               # truncation toward zero, then max(., 0)
+    hi = (center + support + 0.5).to(torch.int64).clamp_max(in_size)
+    for i in range(out_size):
+        j = torch.arange(int(lo[i]), int(hi[i]))
+        w = _cubic_aa((j.to(F32) - center[i] + 0.5) * invscale)
+        m[i, j] = w / w.sum()
+    return m
+
+
+def image_preprocess(src, out, S, mean, std, *, antialias, pre_div=255.0, clip_lo=float("-inf"), clip_hi=float("inf"),
+                     post_div=1.0):
+    H, W = src.shape[0], src.shape[1]
+    v = src.to(F32)
+    v = v.unsqueeze(-1).expand(H, W, 3) if v.dim() == 2 else v
+    v = (v / pre_div).clamp(clip_lo, clip_hi) / post_div
+    RH, RW = (S, int(S * W / H)) if H <= W else (int(S * H / W), S)
+    top, left = int(round((RH - S) / 2.0)), int(round((RW - S) / 2.0))
+    my = _resample_matrix(H, RH, antialias)[top:top + S]                      # only the crop is ever computed
+    mx = _resample_matrix(W, RW, antialias)[left:left + S]
+    r = torch.einsum('yh,hwc,xw->cyx', my, v, mx)
+    out.copy_((r - torch.tensor(mean)[:, None, None]) / torch.tensor(std)[:, None, None])
+    return out
+
+
 BF16_MODE_OPS = ["attention_fwd", "attention_bwd", "cast_bf16", "colsum", "patchify"]
 
 EMULATED_OPS = ["gemm", "expand6", "attention_f32_fwd", "attention_f32_bwd", "layernorm_fwd", "layernorm_bwd",

@@ -64,7 +64,7 @@ def test_ctypes_table_matches_header(built):
 def test_library_loads_and_reports_version(built):
     from missm_b200 import _lib
     L = _lib.lib()
-    assert L.missm_version() == 5
+    assert L.missm_version() == 6
     assert isinstance(L.missm_last_error(), bytes)
 
 
@@ -73,10 +73,11 @@ def test_struct_mirrors_have_the_header_sizes(built):
     from missm_b200._lib import AttnArgs, GemmArgs
     from missm_b200.fusion_ops import FusionSumArgs
     from missm_b200.optim import AdamArgs
+    from missm_b200.ops import PreprocArgs
     prog = r'''
 #include <stdio.h>
 #include "missm_b200.h"
-int main(void) { printf("%zu %zu %zu %zu\n", sizeof(missm_gemm_args), sizeof(missm_attn_args), sizeof(missm_fusion_sum_args), sizeof(missm_adam_args)); return 0; }
+int main(void) { printf("%zu %zu %zu %zu %zu\n", sizeof(missm_gemm_args), sizeof(missm_attn_args), sizeof(missm_fusion_sum_args), sizeof(missm_adam_args), sizeof(missm_preproc_args)); return 0; }
 '''
     import tempfile
     with tempfile.TemporaryDirectory() as d:
@@ -86,4 +87,4 @@ int main(void) { printf("%zu %zu %zu %zu\n", sizeof(missm_gemm_args), sizeof(mis
         subprocess.run(["gcc", "-I", os.path.join(ROOT, "include"), c, "-o", exe], check=True)
         sizes = [int(x) for x in subprocess.run([exe], capture_output=True, text=True, check=True).stdout.split()]
     assert sizes == [ctypes.sizeof(GemmArgs), ctypes.sizeof(AttnArgs), ctypes.sizeof(FusionSumArgs),
-                     ctypes.sizeof(AdamArgs)]
+                     ctypes.sizeof(AdamArgs), ctypes.sizeof(PreprocArgs)]
