@@ -113,7 +113,7 @@ def _pil_rgb_array(path):
     from PIL import Image, ImageFile
     ImageFile.LOAD_TRUNCATED_IMAGES = True                            # processing_image.py:7-8
     img = path if isinstance(path, Image.Image) else Image.open(path)
-    return np.asarray(img)
+    return np.array(img)                # a writable copy: torch.from_numpy refuses to share PIL's read-only buffer quietly
 
 
 class LanguageBindImageProcessor(_ImageLikeProcessor):
