@@ -7,8 +7,11 @@ dropout_prob`), the same return arity per fusion type (train_ddp.py:109-112,232-
 Reference: src/model/baseline.py -- Head :27-39, modal_sum :43-61, modal_concat :65-90,
 modal_regression :94-149, modal_concat_full :153-169, modal_intra_channel_attention :173-203,
 modal_inter_attention :207-236, modal_dedicated_dnn :335-354, modal_distillation :358-380,
-modal_self_distillation :384-418, finetune_model :421-453.  `graph_fusion` / `unified_graph`
-need torch_geometric.SuperGATConv and are not skip-safe: out of scope.
+modal_self_distillation :384-418, finetune_model :421-453; fusion_gcn :11-24, modal_graph_fusion :240-281,
+modal_unified_graph :285-331 (SuperGATConv of torch_geometric -- third party, unpinned, not installed -- is restated
+below from its published algorithm as a dense per-sample computation over the <= 6 modality nodes; these two heads are
+NOT skip-safe -- a missing modality's embedding still enters through its self-loop -- so the towers run the full batch
+for them).
 
 The towers (>99.9 % of the step) run the hand-written CUDA path; `finetune_model.forward` hands
 `missing_index` to the encoder bank so that a tower only computes its PRESENT samples.  The
@@ -236,7 +239,113 @@ class modal_self_distillation(nn.Module):
         return masks, stu, tea, self.head(self.norm(tea))
 
 
+# ------------------------------------------------------------------------------------------------
+# Graph heads (reference :11-24, :240-331).  torch_geometric.nn.SuperGATConv (attention_type 'MX', the default):
+#   h = lin(x) viewed [N, H, C];  for an edge j -> i (self-loops added for every node):
+#   e_ij = leaky_relu( ((h_j . att_l) + (h_i . att_r)) * sigmoid(h_i . h_j), 0.2 );  alpha_i. = softmax_j(e_ij)
+#   out_i = sum_j alpha_ij h_j;  heads concatenated (concat=True) or averaged;  + bias.
+# Its self-supervised edge loss (att_x / att_y, negative sampling) is never read by the reference and is not built.
+# The graphs here are one per sample over the M = len(modality_types) nodes, so the edge lists become a dense
+# [B, M, M] adjacency mask and the scatter-softmax a masked softmax.
+# ------------------------------------------------------------------------------------------------
+class _PygLinear(nn.Module):
+    """torch_geometric.nn.dense.linear.Linear(bias=False): parameter name `weight` [out, in], glorot init."""
+
+    def __init__(self, in_channels, out_channels):
+        super().__init__()
+        self.weight = nn.Parameter(torch.empty(out_channels, in_channels))
+        nn.init.xavier_uniform_(self.weight)
+
+    def forward(self, x):
+        return torch.nn.functional.linear(x, self.weight)
+
+
+class SuperGATConv(nn.Module):
+    def __init__(self, in_channels, out_channels, heads=1, concat=True, negative_slope=0.2):
+        super().__init__()
+        self.heads, self.out_channels, self.concat, self.negative_slope = heads, out_channels, concat, negative_slope
+        self.att_l = nn.Parameter(torch.empty(1, heads, out_channels))
+        self.att_r = nn.Parameter(torch.empty(1, heads, out_channels))
+        self.bias = nn.Parameter(torch.zeros(heads * out_channels if concat else out_channels))
+        self.lin = _PygLinear(in_channels, heads * out_channels)
+        nn.init.xavier_uniform_(self.att_l)
+        nn.init.xavier_uniform_(self.att_r)
+
+    def forward(self, x, adj):
+        """x [B, M, in]; adj bool [B, M, M], adj[b, i, j] = edge j -> i of sample b (self-loops included)."""
+        B, M, _ = x.shape
+        h = self.lin(x).view(B, M, self.heads, self.out_channels)
+        logits = torch.einsum('bihc,bjhc->bhij', h, h)
+        src = (h * self.att_l).sum(-1).permute(0, 2, 1)                  # [B, H, j]
+        dst = (h * self.att_r).sum(-1).permute(0, 2, 1)                  # [B, H, i]
+        e = (src[:, :, None, :] + dst[:, :, :, None]) * logits.sigmoid()
+        e = torch.nn.functional.leaky_relu(e, self.negative_slope)
+        alpha = e.masked_fill(~adj[:, None], float('-inf')).softmax(dim=-1)
+        out = torch.einsum('bhij,bjhc->bihc', alpha, h)
+        out = out.reshape(B, M, self.heads * self.out_channels) if self.concat else out.mean(dim=2)
+        return out + self.bias
+
+
+class fusion_gcn(nn.Module):
+    def __init__(self, in_channels=256, hidden_dim=128, output_dim=256, heads=4):
+        super().__init__()
+        self.gat1 = SuperGATConv(in_channels, hidden_dim, heads=heads, concat=True)
+        self.gat2 = SuperGATConv(hidden_dim * heads, output_dim, heads=1, concat=False)
+        self.act = nn.GELU()
+
+    def forward(self, x, adj):
+        return self.gat2(self.act(self.gat1(x, adj)), adj)
+
+
+def _adjacency(present):
+    """bulid_edge (:270-281) + SuperGATConv's self-loops: i <-> j when BOTH modalities are present, i -> i always."""
+    M = present.shape[1]
+    both = present[:, :, None] & present[:, None, :]
+    return both | torch.eye(M, dtype=torch.bool, device=present.device)[None]
+
+
+class modal_graph_fusion(nn.Module):
+    compaction_safe = False
+
+    def __init__(self, args, output_dims):
+        super().__init__()
+        self.modality_types = args.modality_types
+        self.modal_proj = nn.ModuleDict({m: nn.Linear(args.feature_dims, args.fusion_dim) for m in args.modality_types})
+        self.norm = nn.LayerNorm(args.fusion_dim)
+        self.head = Head(args, args.fusion_dim, output_dims)
+        self.gcn = fusion_gcn()
+
+    def forward(self, batch, missing_index):
+        x = torch.stack([self.modal_proj[m](batch[m]) for m in self.modality_types], dim=1)
+        present = torch.stack([~_miss(missing_index, m) for m in self.modality_types], dim=1)
+        out = self.gcn(x, _adjacency(present)).mean(dim=-2)
+        return self.head(self.norm(out))
+
+
+class modal_unified_graph(nn.Module):
+    compaction_safe = False
+
+    def __init__(self, args, output_dims):
+        super().__init__()
+        self.modality_types = args.modality_types
+        self.norm = nn.LayerNorm(args.fusion_dim)
+        self.head = Head(args, args.fusion_dim, output_dims)
+        self.complete_gcn = fusion_gcn(in_channels=768, hidden_dim=384, output_dim=768)
+        self.fusion_gcn = fusion_gcn(in_channels=768)
+
+    def forward(self, batch, missing_index):
+        feats = torch.stack([batch[m] for m in self.modality_types], dim=1)
+        missing = torch.stack([_miss(missing_index, m) for m in self.modality_types], dim=1)
+        completed = self.complete_gcn(feats, _adjacency(~missing))
+        # the missing modality's embedding is replaced by its reconstruction (:316-318, in place there)
+        feats = torch.where(missing[:, :, None], completed, feats)
+        full = torch.ones_like(missing)
+        out = self.fusion_gcn(feats, _adjacency(full)).mean(dim=-2)
+        return self.head(self.norm(out))
+
+
 _FUSIONS = {
+    'graph_fusion': modal_graph_fusion, 'unified_graph': modal_unified_graph,
     'sum': modal_sum, 'concat': modal_concat, 'regression': modal_regression, 'retrieval': modal_concat_full,
     'intra_attention': modal_intra_channel_attention, 'inter_attention': modal_inter_attention,
     'dedicated_dnn': modal_dedicated_dnn, 'Distill_tea': modal_distillation, 'MTD_stu': modal_distillation,
@@ -249,10 +358,6 @@ class finetune_model(nn.Module):
         super().__init__()
         self.encoder = encoder_model
         self.fusion_type = args.fusion_type
-        if args.fusion_type in ('graph_fusion', 'unified_graph'):
-            raise NotImplementedError(
-                f"fusion_type={args.fusion_type!r} needs torch_geometric.SuperGATConv and is not skip-safe "
-                f"(reference baseline.py:240-331); out of scope of the B200 hot path (SURVEY.md 8(f) rank 4)")
         if args.fusion_type not in _FUSIONS:
             raise ValueError(f"unknown fusion_type {args.fusion_type!r}")
         self.fusion = _FUSIONS[args.fusion_type](args, output_dims)
@@ -265,7 +370,9 @@ class finetune_model(nn.Module):
                 missing_index = missing_index.to(p.device, non_blocking=True)
         # `retrieval` ignores missing_index (the loader substituted a same-label sample and reset the
         # code to 0, data_loader.py:271-276), so nothing may be skipped for it
-        if getattr(self.encoder, 'supports_compaction', False) and self.fusion_type != 'retrieval':
+        # the graph heads read a missing modality's embedding through its self-loop: not skip-safe either
+        skip_safe = self.fusion_type != 'retrieval' and getattr(self.fusion, 'compaction_safe', True)
+        if getattr(self.encoder, 'supports_compaction', False) and skip_safe:
             embedding = self.encoder(data, missing_index=missing_index)   # towers skip missing samples
         else:
             embedding = self.encoder(data)

@@ -306,7 +306,66 @@ def fusion_forward(sd, fusion_type, modality_types, batch, missing_index, pre='f
                 return [~miss[m] for m in modality_types], stu, tea, _head(sd, pre + 'head.', _norm(sd, pre, tea))
             return _head(sd, pre + 'head.', _norm(sd, pre, mp(feats)))
         return feats, _head(sd, pre + 'head.', _norm(sd, pre, mp(feats)))
-    raise ValueError(f"fusion type {fusion_type!r} is out of scope (SURVEY.md section 2 row 3)")
+    if fusion_type == 'graph_fusion':                       # :254-268
+        x = torch.stack([_proj(sd, pre, m, batch[m]) for m in modality_types], 1)
+        outs = []
+        for b in range(x.shape[0]):                         # one graph per sample (Batch.from_data_list keeps them apart)
+            present = [not bool(miss[m][b]) for m in modality_types]
+            outs.append(fusion_gcn(sd, pre + 'gcn.', x[b], build_edge(present)).mean(0))
+        return _head(sd, pre + 'head.', _norm(sd, pre, torch.stack(outs)))
+    if fusion_type == 'unified_graph':                      # :298-329
+        feats = torch.stack([batch[m] for m in modality_types], 1)
+        outs = []
+        for b in range(feats.shape[0]):
+            present = [not bool(miss[m][b]) for m in modality_types]
+            done = fusion_gcn(sd, pre + 'complete_gcn.', feats[b], build_edge(present), hidden=384, heads=4)
+            f = torch.stack([feats[b, i] if present[i] else done[i] for i in range(len(modality_types))])
+            outs.append(fusion_gcn(sd, pre + 'fusion_gcn.', f, build_edge([True] * len(modality_types))).mean(0))
+        return _head(sd, pre + 'head.', _norm(sd, pre, torch.stack(outs)))
+    raise ValueError(f"unknown fusion type {fusion_type!r}")
+
+
+def build_edge(present):
+    """bulid_edge (baseline.py:270-281): both directions of every pair of PRESENT nodes -> int64 [2, E]."""
+    start, end = [], []
+    for i in range(len(present)):
+        for j in range(i + 1, len(present)):
+            if present[i] and present[j]:
+                start.append(i)
+                end.append(j)
+    return torch.tensor([start + end, end + start], dtype=torch.long)
+
+
+def super_gat_conv(sd, pre, x, edge_index, heads, concat, negative_slope=0.2):
+    """torch_geometric.nn.SuperGATConv.forward (third party, unpinned, not installed; call sites baseline.py:14-15,
+    20,22), attention_type='MX', add_self_loops=True, dropout 0 -- restated from its published algorithm as the
+    edge-list / scatter-softmax computation PyG performs.  The self-supervised attention loss it also prepares in
+    training mode (att_x / att_y) is never read by the reference."""
+    N = x.shape[0]
+    w = sd[pre + 'lin.weight']
+    C = w.shape[0] // heads
+    h = F.linear(x, w).view(N, heads, C)
+    keep = edge_index[0] != edge_index[1]                   # remove_self_loops, then add_self_loops
+    loops = torch.arange(N)
+    src = torch.cat([edge_index[0][keep], loops])
+    dst = torch.cat([edge_index[1][keep], loops])
+    x_j, x_i = h[src], h[dst]
+    logits = (x_i * x_j).sum(-1)
+    alpha = (x_j * sd[pre + 'att_l']).sum(-1) + (x_i * sd[pre + 'att_r']).sum(-1)
+    alpha = F.leaky_relu(alpha * logits.sigmoid(), negative_slope)
+    out = torch.zeros_like(h)
+    for i in range(N):                                      # softmax over the incoming edges of node i, then aggregate
+        e = dst == i
+        a = torch.softmax(alpha[e], dim=0)
+        out[i] = (a.unsqueeze(-1) * x_j[e]).sum(0)
+    out = out.reshape(N, heads * C) if concat else out.mean(1)
+    return out + sd[pre + 'bias']
+
+
+def fusion_gcn(sd, pre, x, edge_index, hidden=128, heads=4):
+    """fusion_gcn.forward (baseline.py:11-24): SuperGATConv(heads=4, concat) -> GELU -> SuperGATConv(heads=1, mean)."""
+    x = super_gat_conv(sd, pre + 'gat1.', x, edge_index, heads, True)
+    return super_gat_conv(sd, pre + 'gat2.', F.gelu(x), edge_index, 1, False)
 
 
 def finetune_forward(sd, fusion_type, modality_types, data, missing_index, cfgs, text_cfg, logit_scales,

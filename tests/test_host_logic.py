@@ -84,12 +84,50 @@ def test_product_has_no_cpu_fallback():
         model({'image': {'pixel_values': torch.randn(2, 3, 28, 28)}}, torch.zeros(2, dtype=torch.long))
 
 
-def test_out_of_scope_heads_are_refused():
+def test_unknown_heads_are_refused():
     from src.model.baseline import finetune_model
-    args = types.SimpleNamespace(fusion_type='graph_fusion', modality_types=['image'], feature_dims=8, fusion_dim=8,
+    args = types.SimpleNamespace(fusion_type='no_such_head', modality_types=['image'], feature_dims=8, fusion_dim=8,
                                  dropout_prob=0.0)
-    with pytest.raises(NotImplementedError):
+    with pytest.raises(ValueError):
         finetune_model(args, 3, torch.nn.Identity())
+
+
+@pytest.mark.parametrize("fusion", ["graph_fusion", "unified_graph"])
+def test_graph_heads_dense_form_matches_edge_list_oracle(fusion):
+    """The graph heads (reference baseline.py:240-331) as dense per-sample masked attention vs the oracle's edge-list
+    restatement of torch_geometric's SuperGATConv: every missing pattern incl. an isolated node; not skip-safe, so the
+    bank must NOT be asked to compact for them.  (torch_geometric is absent: parity unpinned for that third party.)"""
+    from src.model import baseline as B
+    mods = ['language', 'video', 'audio', 'image']
+    P, Fd = 768, 256                                   # fusion_gcn() hard-codes 256 / 768 (:253, :293-294)
+    args = types.SimpleNamespace(fusion_type=fusion, modality_types=mods, feature_dims=P, fusion_dim=Fd, dropout_prob=0.0)
+    head = B._FUSIONS[fusion](args, 3).eval()
+    assert head.compaction_safe is False
+    sd = R.synth_state_dict([(k, tuple(v.shape)) for k, v in head.state_dict().items()])
+    for k in sd:
+        if k.endswith('att_l') or k.endswith('att_r'):
+            sd[k] = R.synth_param(k, sd[k].shape, 0.3)
+    head.load_state_dict(sd)
+    g = torch.Generator().manual_seed(0)
+    emb = {m: torch.randn(6, P, generator=g) for m in mods}
+    mi = torch.tensor([0, 1, 2, 3, 4, 0])
+    with torch.no_grad():
+        out = head({k: v.clone() for k, v in emb.items()}, mi)
+        ref = R.fusion_forward({'fusion.' + k: v for k, v in sd.items()}, fusion, mods, emb, mi)
+    assert ((out - ref).norm() / ref.norm()).item() < 1e-5
+    # a missing modality's embedding still matters (self-loop): changing it changes the logits of that sample only
+    emb2 = {k: v.clone() for k, v in emb.items()}
+    emb2['video'][2] += 1.0
+    with torch.no_grad():
+        out2 = head(emb2, mi)
+    changed = (out2 - out).abs().max(dim=1).values > 1e-6
+    # (unified_graph replaces the missing embedding by the completion GCN's output for that node, :316-318 -- but
+    #  a node without present neighbours only has its self-loop, so that output is a function of the same embedding)
+    assert changed.tolist() == [False, False, True, False, False, False]
+    # names follow the reference's module tree
+    keys = set(head.state_dict())
+    pre = 'gcn.' if fusion == 'graph_fusion' else 'complete_gcn.'
+    assert {pre + 'gat1.att_l', pre + 'gat1.att_r', pre + 'gat1.bias', pre + 'gat1.lin.weight', pre + 'gat2.lin.weight'} <= keys
 
 
 def test_return_arity_per_fusion_type():
