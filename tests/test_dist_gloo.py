@@ -77,6 +77,80 @@ def test_two_rank_host_logic():
         assert torch.allclose(torch.tensor(res[0]["grads"][n]), torch.tensor(res[1]["grads"][n])), n
 
 
+def _worker_model(rank, world, port, q, lora_r):
+    """The PRODUCT model (tiny towers + `sum` head, optionally LoRA-wrapped) under DDP exactly as train_ddp.py:189
+    wraps it, over torch stand-ins of the C ABI (tests/ops_emulation.py): rank 1's batch has NO sample with an image,
+    so its image tower runs zero rows and must still hand DDP a gradient for every trainable parameter."""
+    sys.path.insert(0, os.path.join(ROOT, "missm-benchmark_b200"))
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    sys.path.insert(0, HERE)
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    import restatement as R
+    import ops_emulation as E
+    from missm_b200 import shapes
+    v = dict(hidden_size=128, intermediate_size=256, num_hidden_layers=1, num_attention_heads=2, patch_size=14,
+             image_size=28, lora_r=lora_r, lora_alpha=16)
+    cfgs = {'image': R.vision_config(**v), 'depth': R.vision_config(**v)}
+    tcfg = R.text_config(hidden_size=128, intermediate_size=256, num_hidden_layers=1, num_attention_heads=2, vocab_size=50)
+    modal = ['image', 'depth']
+    model = shapes.build_finetune(cfgs, tcfg, modal, 'sum', 3, 32, 16)
+    shapes.load_named(model, R.synth_state_dict([(k, tuple(t.shape)) for k, t in model.state_dict().items()]))
+    for n, p in model.named_parameters():
+        if 'language' in n:
+            p.requires_grad_(False)                    # registered (text tower of the last model) but unused here
+    B = 4
+    data = R.synth_inputs(modal, B, cfgs, tcfg, seed=rank)
+    mi = torch.tensor([0, 5, 0, 4]) if rank == 0 else torch.tensor([4, 4, 4, 4])   # rank 1: image missing everywhere
+    labels = torch.arange(B) % 3
+    out = {}
+    with E.emulated_fp32_mode(precision="bf16", wide_bf16=True):
+        ddp = torch.nn.parallel.DistributedDataParallel(model, broadcast_buffers=True, find_unused_parameters=False)
+        loss = torch.nn.functional.cross_entropy(ddp(data, mi), labels)
+        loss.backward()
+    trainable = [(n, p) for n, p in model.named_parameters() if p.requires_grad]
+    out["all_have_grad"] = all(p.grad is not None for _, p in trainable)
+    out["frozen_have_none"] = all(p.grad is None for _, p in model.named_parameters() if not p.requires_grad)
+    out["n_trainable"] = len(trainable)
+    out["grads"] = {n: p.grad.flatten()[:64].tolist() for n, p in trainable}
+    out["loss"] = float(loss)
+    q.put((rank, out))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def _run_two_ranks(target, *extra):
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=target, args=(r, 2, port, q) + extra) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = dict(q.get(timeout=300) for _ in range(2))
+    for p in procs:
+        p.join(timeout=120)
+        assert p.exitcode == 0
+    return res
+
+
+def test_two_rank_product_model_with_an_empty_tower():
+    res = _run_two_ranks(_worker_model, 0)
+    assert res[0]["all_have_grad"] and res[1]["all_have_grad"] and res[0]["loss"] != res[1]["loss"]
+    for n in res[0]["grads"]:                          # all-reduced: identical on both ranks
+        assert torch.allclose(torch.tensor(res[0]["grads"][n]), torch.tensor(res[1]["grads"][n]), rtol=1e-5, atol=1e-7), n
+
+
+def test_two_rank_lora_model_frozen_encoder():
+    """LoRA-wrapped towers under DDP: the frozen encoder weights are not DDP parameters and get no gradient, the
+    adapters (and embeddings, projections, head) are reduced; the empty tower on rank 1 does not stall the reducer."""
+    res = _run_two_ranks(_worker_model, 2)
+    assert res[0]["all_have_grad"] and res[1]["all_have_grad"]
+    assert res[0]["frozen_have_none"] and res[1]["frozen_have_none"]
+    assert any('.lora_A.' in n for n in res[0]["grads"]) and not any('mlp.fc1' in n for n in res[0]["grads"])
+    for n in res[0]["grads"]:
+        assert torch.allclose(torch.tensor(res[0]["grads"][n]), torch.tensor(res[1]["grads"][n]), rtol=1e-5, atol=1e-7), n
+
+
 def test_reference_arm_under_torchrun_prints_one_line():
     port = _free_port()
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
