@@ -153,7 +153,7 @@ class FusedAdam(torch.optim.Optimizer):
         a.exp_avg, a.exp_avg_sq = tab['exp_avg'].data_ptr(), tab['exp_avg_sq'].data_ptr()
         # bf16 GEMM-operand copies the forward path keeps of these parameters: rewritten by the same pass
         # (saves the 6 B / element cast kernels of the next forward); anything not eligible rebuilds itself
-        a.bf16_out, entries = None, []
+        a.bf16_out, entries, dst = None, [], {}
         if self.refresh_operands:
             dst, entries = ag.plan_operand_refresh(touched)
             if dst:
@@ -167,7 +167,7 @@ class FusedAdam(torch.optim.Optimizer):
         a.beta1, a.beta2, a.eps, a.weight_decay = beta1, beta2, group['eps'], group['weight_decay']
         a.zero_grads = 0
         keep += [d_g, d_sb]
-        tab['touched'], tab['entries'] = touched, entries
+        tab['touched'], tab['entries'], tab['rewritten'] = touched, entries, list(dst.values())
         return a, keep, tab
 
     def _launch(self, a, tab):
@@ -192,8 +192,10 @@ class FusedAdam(torch.optim.Optimizer):
             # the kernel wrote through raw pointers: advance the parameters' version counters (host-only, no launch)
             # so that everything keyed on them -- the cached bf16 GEMM-operand copies of autograd.cached_weight,
             # autograd's saved-tensor checks -- sees the update exactly as after an in-place torch op
-            touched = tuple(tab['touched'])
-            torch._C._autograd._unsafe_set_version_counter(touched, tuple(p._version + 1 for p in touched))
+            # (the rewritten bf16 copies too: a backward over a graph recorded BEFORE this step must fail loudly, as it
+            #  does with torch's own in-place update, instead of silently using the new weights)
+            touched = tuple(tab['touched']) + tuple(tab['rewritten'])
+            torch._C._autograd._unsafe_set_version_counter(touched, tuple(t._version + 1 for t in touched))
             ag.restamp(tab['entries'])
         return loss
 
