@@ -108,3 +108,34 @@ def test_precision_switch():
             ag.set_precision("fp16")
     finally:
         ag.set_precision(old)
+
+
+def test_product_blocks_host_algebra_matches_reference_golden(tiny):
+    """The PRODUCT (bf16-mode) autograd Functions -- AttnBlockFn, MlpBlockFn, VisionEmbedFn, TextEmbedFn, PoolProjFn,
+    ScatterZeroFn with mask compaction, the side channel of bf16 gradient copies and fused bias sums -- over the ABI
+    stand-ins with every "bf16" buffer widened to fp32: all five towers + text + `sum` head must reproduce the
+    reference's embeddings, loss and gradients at fp32 accuracy, i.e. every formula and operand layout of the path
+    the B200 runs is right independently of bf16 rounding (which the GPU tests bound at 1e-2)."""
+    meta = tiny['meta']
+    modal_types = ['language'] + meta['modals']
+    model, cfgs, tcfg = _make(meta, modal_types, 'sum')
+    model.train()
+    data = R.synth_inputs(modal_types, meta['B'], cfgs, tcfg, seed=0)
+    mi = tiny['missing_index']
+    with E.emulated_fp32_mode(precision="bf16", wide_bf16=True):
+        with torch.no_grad():
+            emb = model.encoder(data)
+        logits = model(data, mi)
+        loss = torch.nn.functional.cross_entropy(logits, tiny['labels'])
+        loss.backward()
+    for m in modal_types:
+        assert rel(emb[m], tiny[f'emb/{m}']) < TOL_F32, (m, rel(emb[m], tiny[f'emb/{m}']))
+    assert rel(logits, tiny['logits/sum']) < 1e-4
+    assert abs(loss.item() - tiny['loss/sum'].item()) < TOL_F32 * abs(tiny['loss/sum'].item())
+    params = dict(model.named_parameters())
+    for k, v in tiny.items():
+        if k.startswith('grad/') and v.norm() > 1e-6:
+            assert rel(params[k[5:]].grad, v) < TOL_F32_GRAD, (k, rel(params[k[5:]].grad, v))
+    for n, ref in tiny['grad_norms'].items():
+        if ref > 1e-6:
+            assert abs(params[n].grad.norm().item() - ref) < 2e-4 * ref, n
