@@ -275,26 +275,31 @@ def run_gpu_arm(a):
 
     for _ in range(max(a.warmup, 3)):
         step_resident()
+    from missm_b200 import _lib
+    L = ops.lib()
     sampler = ClockSampler(local) if rank == 0 else None
-    ops.LAUNCHES[0] = 0
+    L.missm_launch_count(1)                    # the library counts its own kernel launches
+    calls0 = _lib.CALLS[0]
     ms = timed(step_resident, a.steps)
-    launches = ops.LAUNCHES[0]
+    launches = int(L.missm_launch_count(0))
+    binding_calls = (_lib.CALLS[0] - calls0) / a.steps
     host_issue_ms = host_ms[0]
     clocks = sampler.stop() if sampler else None
     samples_per_s = world * B * a.steps / (ms / 1e3)
 
     # roofline of the dominant kernel (tcgen05 GEMM): CUDA events around every GEMM launch of one
     # more step on the launching stream (kept out of the headline so the events cost nothing there)
-    ops.GEMM_TIMING = []
+    import ctypes
     streams_on = model.encoder.tower_streams
     model.encoder.tower_streams = False       # one stream: every GEMM is timed alone, not overlapped with another tower's
+    L.missm_gemm_profile(1)
     step_resident()
     torch.cuda.synchronize()
+    L.missm_gemm_profile(0)
     model.encoder.tower_streams = streams_on
-    g_ms = sum(e0.elapsed_time(e1) for e0, e1, _ in ops.GEMM_TIMING)
-    g_flop = sum(f for _, _, f in ops.GEMM_TIMING)
-    n_gemm = len(ops.GEMM_TIMING)
-    ops.GEMM_TIMING = None
+    g_ms_c, g_flop_c, n_gemm_c = ctypes.c_double(), ctypes.c_double(), ctypes.c_int64()
+    L.missm_gemm_profile_read(ctypes.byref(g_ms_c), ctypes.byref(g_flop_c), ctypes.byref(n_gemm_c))
+    g_ms, g_flop, n_gemm = g_ms_c.value, g_flop_c.value, n_gemm_c.value
     pk, pk_src = peaks()
     peak_tf = pk.get("bf16_tflops_sustained", pk["bf16_tflops"])
     ach_tf = g_flop / (g_ms / 1e3) / 1e12 if g_ms > 0 else 0.0
@@ -346,7 +351,7 @@ def run_gpu_arm(a):
                        "missing_samples": n_missing, "fusion": "sum", "layers": a.layers, "tower_streams": bool(model.encoder.tower_streams),
                        "ddp": (None if world == 1 else "DistributedDataParallel as train_ddp.py:189" +
                                (" + gradient_as_bucket_view (measurement switch)" if os.environ.get("MISSM_BENCH_BUCKET_VIEW") else "")),
-                       "host_issue_ms_per_step": host_issue_ms,
+                       "host_issue_ms_per_step": host_issue_ms, "binding_calls_per_step": binding_calls,
                        "variant": "; ".join(variant) if variant else None,
                        "step": "zero_grad + forward + CrossEntropy + backward (DDP allreduce at N>1); " +
                                ("optimizer excluded (metric is fwd+bwd)" if opt is None else "optimizer.step() included"),

@@ -24,8 +24,8 @@
 extern "C" {
 #endif
 
-#define MISSM_ABI_VERSION 6   /* 3: missm_set_persistent_sms; 4: fp32 verification mode; 5: missm_adam_multi;
-                                 6: missm_image_preprocess */
+#define MISSM_ABI_VERSION 7   /* 3: missm_set_persistent_sms; 4: fp32 verification mode; 5: missm_adam_multi;
+                                 6: missm_image_preprocess; 7: residual-block drivers, launch counter, GEMM profile */
 
 int missm_version(void);
 const char* missm_last_error(void);
@@ -302,6 +302,104 @@ typedef struct missm_preproc_args {
   float std_[3];
 } missm_preproc_args;
 int missm_image_preprocess(const missm_preproc_args* args, void* stream);
+
+/* ---------------------------------------------------------------------------------------
+ * Residual-block drivers (csrc/blocks.cu): ONE call issues every kernel of one residual block of
+ * CLIPEncoderLayer.forward (languagebind/image/modeling_image.py:105-127 temporal attention, :129-134 temporal MLP,
+ * :137-146 spatial attention, :148-151 MLP; the autograd twins run at train_ddp.py:253) into caller-provided
+ * memory, so the host pays one binding call per block instead of one per kernel (round 1: 1 936 binding calls and
+ * 98.6 ms of host time per 101.6 ms step).  Nothing allocates; `saved` lives from forward to backward, `scratch` only
+ * during the backward call (stream-ordered: the caller may recycle it as soon as the call returns if the next user
+ * is on the same stream).  missm_*_block_sizes fills {saved bytes, scratch bytes, grads floats}.
+ *
+ * attention block:  out = x' + OutProj(Attention(QKV(LN(x'))))      x' = x + add_rows[(r / add_div) % add_period]
+ *   w_qkv bf16 [3D, ldw_qkv] = q | k | v rows, b_qkv f32 [3D]; w_o bf16 [D, ldw_o], b_o f32 [D]; the q block of the
+ *   projection is scaled by head_dim^-0.5 in the GEMM epilogue; sequence layout / masks as missm_attn_args.
+ *   LoRA (lora_r > 0; peft Linear y = W x + b + s B(A x), reference convert_to_lora, modeling_image.py:775-793), with
+ *   R3 = pad8(3 r), R1 = pad8(r): w_qkv = [W | s B_cat] (ldw_qkv >= D + R3), wb_qkv bf16 [3D + R3, D] = [W ; A_cat]
+ *   row-stacked; w_o = [W_o | s B_o] (ldw_o >= D + R1), wb_o bf16 [D + R1, D] = [W_o ; A_o].
+ *   grads (floats, in this order): d_ln_w [D], d_ln_b [D], dx_colsum [D], d_w_qkv [3D, D], d_b_qkv [3D],
+ *   d_w_o [D, D], d_b_o [D], d_add_rows [add_period, D] (if add_rows), then with LoRA d_A_cat [R3, D],
+ *   d_sB_cat [3D, R3], d_A_o [R1, D], d_sB_o [D, R1] (gradients w.r.t. the PACKED operands: the caller slices the
+ *   q / k / v diagonal blocks and multiplies the B parts by s).  wgrad = 0 (frozen encoder): d_w_*, d_b_* are not
+ *   computed.  dx_colsum = column sums of dx = bias gradient of the Linear that produced x.
+ *   Backward inputs: d_out f32 [M, D] (required), d_out_bf16 (optional bf16 copy [M, D]; else made here),
+ *   d_out_colsum_given: 1 = the caller already owns d_b_o (the dx_colsum of the block that consumed `out`), so it is
+ *   not recomputed.  Outputs: dx f32 [M, D], dx_bf16 [M, D].
+ * MLP block:  out = x + fc2(quick_gelu(fc1(LN(x))));  w1 bf16 [F, D], w2 bf16 [D, F];
+ *   grads: d_ln_w [D], d_ln_b [D], dx_colsum [D], d_w1 [F, D], d_b1 [F], d_w2 [D, F], d_b2 [D].
+ * ------------------------------------------------------------------------------------- */
+typedef struct missm_attn_block_args {
+  int32_t M, D, H;
+  float eps;
+  int64_t seq_outer, seq_inner, tok_stride;
+  int32_t N, n_seq, s_in, causal, mask_div;
+  const int64_t* key_mask;
+  const int32_t* mask_rows;
+  const float* add_rows;
+  int32_t add_period, add_div;
+  const float* ln_w;
+  const float* ln_b;
+  const void* w_qkv;
+  const float* b_qkv;
+  const void* w_o;
+  const float* b_o;
+  int32_t ldw_qkv, ldw_o;
+  int32_t lora_r;
+  const void* wb_qkv;
+  const void* wb_o;
+  const float* x;
+  float* out;
+  void* saved;
+  /* backward */
+  const float* d_out;
+  const void* d_out_bf16;
+  int32_t d_out_colsum_given;
+  int32_t wgrad;
+  float* dx;
+  void* dx_bf16;
+  float* grads;
+  void* scratch;
+} missm_attn_block_args;
+int missm_attn_block_sizes(const missm_attn_block_args* args, int64_t sizes[3]);
+int missm_attn_block_fwd(const missm_attn_block_args* args, void* stream);
+int missm_attn_block_bwd(const missm_attn_block_args* args, void* stream);
+
+typedef struct missm_mlp_block_args {
+  int32_t M, D, F;
+  float eps;
+  const float* ln_w;
+  const float* ln_b;
+  const void* w1;
+  const float* b1;
+  const void* w2;
+  const float* b2;
+  const float* x;
+  float* out;
+  void* saved;
+  /* backward */
+  const float* d_out;
+  const void* d_out_bf16;
+  int32_t d_out_colsum_given;
+  int32_t wgrad;
+  float* dx;
+  void* dx_bf16;
+  float* grads;
+  void* scratch;
+} missm_mlp_block_args;
+int missm_mlp_block_sizes(const missm_mlp_block_args* args, int64_t sizes[3]);
+int missm_mlp_block_fwd(const missm_mlp_block_args* args, void* stream);
+int missm_mlp_block_bwd(const missm_mlp_block_args* args, void* stream);
+
+/* ---------------------------------------------------------------------------------------
+ * Measurement hooks (bench.py): the number of kernels this library has launched since the last reset, and CUDA
+ * events around every missm_gemm_bf16 launch (on the launching stream) while the profile is on.
+ * missm_gemm_profile(1) starts (and clears), missm_gemm_profile(0) stops; missm_gemm_profile_read synchronises the
+ * recorded events and returns the summed milliseconds, 2*M*N*K flops and launch count.
+ * ------------------------------------------------------------------------------------- */
+int64_t missm_launch_count(int32_t reset);
+int missm_gemm_profile(int32_t on);
+int missm_gemm_profile_read(double* ms, double* flop, int64_t* launches);
 
 #ifdef __cplusplus
 }

@@ -534,7 +534,7 @@ extern "C" int missm_attention_fwd(const missm_attn_args* a, void* stream) {
   if (int rc = fill_params(p, a)) return rc;
   MISSM_REQUIRE(p.qkv && p.out, "attention_fwd: null tensor");
   dim3 grid((p.N + TILE - 1) / TILE, p.H, p.n_seq);
-  attn_fwd_kernel<<<grid, kAttnThreads, 0, static_cast<cudaStream_t>(stream)>>>(p);
+  attn_fwd_kernel<<<grid, kAttnThreads, 0, static_cast<cudaStream_t>(stream)>>>(p); note_launch();
   MISSM_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
@@ -554,10 +554,10 @@ extern "C" int missm_attention_bwd(missm_attn_args* a, void* stream) {
     const int rc = attention_bwd_tc(a, st);   // tcgen05 path for the shapes it covers (computes delta itself)
     if (rc >= 0) return rc;
   }
-  attn_delta_kernel<<<dgrid, 256, 0, st>>>(p);
+  attn_delta_kernel<<<dgrid, 256, 0, st>>>(p); note_launch();
   dim3 grid((p.N + TILE - 1) / TILE, p.H, p.n_seq);
-  attn_bwd_dkv_kernel<<<grid, kAttnThreads, 0, st>>>(p);
-  attn_bwd_dq_kernel<<<grid, kAttnThreads, 0, st>>>(p);
+  attn_bwd_dkv_kernel<<<grid, kAttnThreads, 0, st>>>(p); note_launch();
+  attn_bwd_dq_kernel<<<grid, kAttnThreads, 0, st>>>(p); note_launch();
   MISSM_CHECK_CUDA(cudaGetLastError());
   return 0;
 }

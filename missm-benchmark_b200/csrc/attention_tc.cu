@@ -436,7 +436,7 @@ int attention_fwd_tc(const missm_attn_args* a, cudaStream_t stream) {
     MISSM_CHECK_CUDA(cudaMalloc(&d, nb));
     MISSM_CHECK_CUDA(cudaMemsetAsync(d, 0, nb, stream));
     p.trace = d;
-    attn_fwd_tc_kernel<<<grid, FW_THREADS, smem, stream>>>(tm128, tm16, p);
+    attn_fwd_tc_kernel<<<grid, FW_THREADS, smem, stream>>>(tm128, tm16, p); note_launch();
     MISSM_CHECK_CUDA(cudaStreamSynchronize(stream));
     long long* h = static_cast<long long*>(malloc(nb));
     MISSM_CHECK_CUDA(cudaMemcpy(h, d, nb, cudaMemcpyDeviceToHost));
@@ -449,7 +449,7 @@ int attention_fwd_tc(const missm_attn_args* a, cudaStream_t stream) {
     cudaFree(d);
     return 0;
   }
-  attn_fwd_tc_kernel<<<grid, FW_THREADS, smem, stream>>>(tm128, tm16, p);
+  attn_fwd_tc_kernel<<<grid, FW_THREADS, smem, stream>>>(tm128, tm16, p); note_launch();
   MISSM_CHECK_CUDA(cudaGetLastError());
   return 0;
 }

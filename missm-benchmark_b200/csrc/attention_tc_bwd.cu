@@ -674,7 +674,7 @@ int attention_bwd_tc(const missm_attn_args* a, cudaStream_t stream) {
     d.qkv = p.qkv, d.out = static_cast<const __nv_bfloat16*>(a->out), d.d_out = p.d_out, d.lse = a->lse;
     d.delta = a->delta, d.dqkv = p.dqkv, d.ld_qkv = a->ld_qkv, d.ld_o = a->ld_o;
     d.N = a->N, d.H = a->H, d.D = a->D, d.tail = tail;
-    attn_delta_tail_kernel<<<p.n_items, DT_THREADS, 0, stream>>>(d);
+    attn_delta_tail_kernel<<<p.n_items, DT_THREADS, 0, stream>>>(d); note_launch();
   };
   p.trace = nullptr;
   const char* trace_path = getenv("MISSM_ATTN_TRACE");   // debugging aid: dumps CTA 0's event clocks (synchronises!)
@@ -686,9 +686,9 @@ int attention_bwd_tc(const missm_attn_args* a, cudaStream_t stream) {
     p.trace = d;
     launch_delta(0);
     p.tail = 0, p.nt = (a->N + 127) / 128;     // tracing walks all tiles
-    attn_bwd_tc_kernel<true><<<grid, BW_THREADS, smem, stream>>>(tm128, tm16, td128, td16, p);
+    attn_bwd_tc_kernel<true><<<grid, BW_THREADS, smem, stream>>>(tm128, tm16, td128, td16, p); note_launch();
     p.trace = d + 3 * 330 * 3;
-    attn_bwd_tc_kernel<false><<<grid, BW_THREADS, smem, stream>>>(tm128, tm16, td128, td16, p);
+    attn_bwd_tc_kernel<false><<<grid, BW_THREADS, smem, stream>>>(tm128, tm16, td128, td16, p); note_launch();
     MISSM_CHECK_CUDA(cudaStreamSynchronize(stream));
     long long* h = static_cast<long long*>(malloc(nb));
     MISSM_CHECK_CUDA(cudaMemcpy(h, d, nb, cudaMemcpyDeviceToHost));
@@ -706,8 +706,8 @@ int attention_bwd_tc(const missm_attn_args* a, cudaStream_t stream) {
   // DQ: its odd QUERY row is computed by warps 2-3 of the kernel itself
   AttnBwdTcParams pk = p;
   pk.tail = 0;
-  attn_bwd_tc_kernel<true><<<grid, BW_THREADS, smem, stream>>>(tm128, tm16, td128, td16, pk);
-  attn_bwd_tc_kernel<false><<<grid, BW_THREADS, smem, stream>>>(tm128, tm16, td128, td16, p);
+  attn_bwd_tc_kernel<true><<<grid, BW_THREADS, smem, stream>>>(tm128, tm16, td128, td16, pk); note_launch();
+  attn_bwd_tc_kernel<false><<<grid, BW_THREADS, smem, stream>>>(tm128, tm16, td128, td16, p); note_launch();
   MISSM_CHECK_CUDA(cudaGetLastError());
   return 0;
 }

@@ -79,7 +79,7 @@ extern "C" int missm_compact_mask(const int64_t* missing_index, int32_t Bn, cons
   CompactCodes cc;
   for (int i = 0; i < MISSM_MAX_TOWERS; ++i) cc.code[i] = i < n_towers ? codes_host[i] : -1;
   compact_mask_kernel<<<1, 32 * n_towers, 0, static_cast<cudaStream_t>(stream)>>>(
-      missing_index, Bn, cc, n_towers, present_idx, slot_of, counts);
+      missing_index, Bn, cc, n_towers, present_idx, slot_of, counts); note_launch();
   MISSM_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
@@ -91,7 +91,7 @@ extern "C" int missm_scatter_rows_zero(const float* src, const int32_t* slot_of,
   const long total = static_cast<long>(Bn) * (P / 4);
   int grid = static_cast<int>((total + 255) / 256);
   if (grid > 8 * kNumSMs) grid = 8 * kNumSMs;
-  scatter_rows_zero_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(src, slot_of, dst, Bn, P);
+  scatter_rows_zero_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(src, slot_of, dst, Bn, P); note_launch();
   MISSM_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
@@ -104,7 +104,7 @@ extern "C" int missm_gather_rows(const void* src, const int32_t* idx, void* dst,
   int grid = static_cast<int>((total + 255) / 256);
   if (grid > 16 * kNumSMs) grid = 16 * kNumSMs;
   gather_rows_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(
-      static_cast<const uint4*>(src), idx, static_cast<uint4*>(dst), n_rows, vec);
+      static_cast<const uint4*>(src), idx, static_cast<uint4*>(dst), n_rows, vec); note_launch();
   MISSM_CHECK_CUDA(cudaGetLastError());
   return 0;
 }

@@ -314,7 +314,7 @@ extern "C" int missm_cast_f32_bf16(const float* src, int64_t ld_src, void* dst, 
   MISSM_REQUIRE(cols_dst % 4 == 0 && ld_dst % 4 == 0 && cols_dst >= cols, "cast: bad dst cols %d", cols_dst);
   const long total = static_cast<long>(rows) * (cols_dst / 4);
   cast_f32_bf16_kernel<<<grid_for(total, 256), 256, 0, ST(stream)>>>(
-      src, ld_src, static_cast<__nv_bfloat16*>(dst), ld_dst, rows, cols, cols_dst);
+      src, ld_src, static_cast<__nv_bfloat16*>(dst), ld_dst, rows, cols, cols_dst); note_launch();
   MISSM_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
@@ -336,8 +336,8 @@ extern "C" int missm_colsum_bf16(const void* x, int64_t ldx, int32_t M, int32_t 
   const int rows_per_block = (M + R - 1) / R;
   dim3 grid((N + 255) / 256, R), block(32, kColsumRows);
   colsum_bf16_kernel<<<grid, block, 0, ST(stream)>>>(static_cast<const __nv_bfloat16*>(x), ldx, M, N,
-                                                    partial, rows_per_block);
-  reduce_rows_kernel<<<(N + 31) / 32, dim3(32, 8), 0, ST(stream)>>>(partial, R, N, out);
+                                                    partial, rows_per_block); note_launch();
+  reduce_rows_kernel<<<(N + 31) / 32, dim3(32, 8), 0, ST(stream)>>>(partial, R, N, out); note_launch();
   MISSM_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
@@ -349,12 +349,13 @@ extern "C" int missm_patchify(const float* pixels, const int32_t* sample_index, 
   const int gh = H / ps, gw = W / ps, K = C * ps * ps;
   MISSM_REQUIRE(Kpad >= K && Kpad % 8 == 0 && T >= 1, "patchify: Kpad=%d K=%d T=%d", Kpad, K, T);
   const long rows = static_cast<long>(Bn) * T * gh * gw;
-  if (Kpad > K)
+  if (Kpad > K) {
     zero_pad_cols_kernel<<<grid_for(rows * (Kpad - K), 256), 256, 0, ST(stream)>>>(
-        static_cast<__nv_bfloat16*>(patches), rows, K, Kpad);
+        static_cast<__nv_bfloat16*>(patches), rows, K, Kpad); note_launch();
+  }
   const long warps = static_cast<long>(Bn) * T * C * gh * ps;
   patchify_kernel<__nv_bfloat16><<<grid_for(warps * 32, 256), 256, 0, ST(stream)>>>(
-      pixels, sample_index, static_cast<__nv_bfloat16*>(patches), Bn, C, T, H, W, ps, gh, gw, Kpad);
+      pixels, sample_index, static_cast<__nv_bfloat16*>(patches), Bn, C, T, H, W, ps, gh, gw, Kpad); note_launch();
   MISSM_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
@@ -369,7 +370,7 @@ extern "C" int missm_patchify_f32(const float* pixels, const int32_t* sample_ind
   MISSM_REQUIRE(T >= 1 && Kpad >= K, "patchify_f32: T=%d Kpad=%d K=%d", T, Kpad, K);
   const long warps = static_cast<long>(Bn) * T * C * gh * ps;
   patchify_kernel<float><<<grid_for(warps * 32, 256), 256, 0, ST(stream)>>>(pixels, sample_index, patches, Bn, C, T, H,
-                                                                            W, ps, gh, gw, Kpad);
+                                                                            W, ps, gh, gw, Kpad); note_launch();
   MISSM_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
@@ -377,7 +378,7 @@ extern "C" int missm_patchify_f32(const float* pixels, const int32_t* sample_ind
 extern "C" int missm_cls_rows(const float* cls, const float* pos, float* tok, int32_t Bn,
                               int32_t ntok, int32_t D, void* stream) {
   if (Bn == 0) return 0;
-  cls_rows_kernel<<<grid_for(static_cast<long>(Bn) * D, 256), 256, 0, ST(stream)>>>(cls, pos, tok, Bn, ntok, D);
+  cls_rows_kernel<<<grid_for(static_cast<long>(Bn) * D, 256), 256, 0, ST(stream)>>>(cls, pos, tok, Bn, ntok, D); note_launch();
   MISSM_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
@@ -386,7 +387,7 @@ extern "C" int missm_embed_bwd(const float* dtok, float* dpos, void* dpatch_bf16
                                int32_t ntok, int32_t D, void* stream) {
   MISSM_REQUIRE(D % 4 == 0, "embed_bwd: D=%d", D);
   embed_bwd_kernel<<<grid_for(static_cast<long>(ntok) * (D / 4), 128), 128, 0, ST(stream)>>>(
-      dtok, dpos, static_cast<__nv_bfloat16*>(dpatch_bf16), Bn, ntok, D);
+      dtok, dpos, static_cast<__nv_bfloat16*>(dpatch_bf16), Bn, ntok, D); note_launch();
   MISSM_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
@@ -394,14 +395,14 @@ extern "C" int missm_embed_bwd(const float* dtok, float* dpos, void* dpatch_bf16
 extern "C" int missm_frame_mean(const float* in, void* out, int32_t out_bf16, int32_t Bn, int32_t T,
                                 int32_t D, void* stream) {
   if (Bn == 0) return 0;
-  frame_mean_kernel<<<grid_for(static_cast<long>(Bn) * D, 256), 256, 0, ST(stream)>>>(in, out, out_bf16, Bn, T, D);
+  frame_mean_kernel<<<grid_for(static_cast<long>(Bn) * D, 256), 256, 0, ST(stream)>>>(in, out, out_bf16, Bn, T, D); note_launch();
   MISSM_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
 extern "C" int missm_frame_mean_bwd(const float* dout, float* din, int32_t Bn, int32_t T, int32_t D,
                                     void* stream) {
   if (Bn == 0) return 0;
-  frame_mean_bwd_kernel<<<grid_for(static_cast<long>(Bn) * T * D, 256), 256, 0, ST(stream)>>>(dout, din, Bn, T, D);
+  frame_mean_bwd_kernel<<<grid_for(static_cast<long>(Bn) * T * D, 256), 256, 0, ST(stream)>>>(dout, din, Bn, T, D); note_launch();
   MISSM_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
@@ -409,7 +410,7 @@ extern "C" int missm_frame_mean_bwd(const float* dout, float* din, int32_t Bn, i
 extern "C" int missm_l2norm_scale_fwd(const float* x, float* y, float* inv_norm, float scale,
                                       int32_t Bn, int32_t P, void* stream) {
   if (Bn == 0) return 0;
-  l2norm_scale_fwd_kernel<<<(Bn * 32 + 127) / 128, 128, 0, ST(stream)>>>(x, y, inv_norm, scale, Bn, P);
+  l2norm_scale_fwd_kernel<<<(Bn * 32 + 127) / 128, 128, 0, ST(stream)>>>(x, y, inv_norm, scale, Bn, P); note_launch();
   MISSM_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
@@ -417,7 +418,7 @@ extern "C" int missm_l2norm_scale_bwd(const float* dy, const float* x, const flo
                                       float scale, void* dx, int32_t dx_bf16, int32_t Bn, int32_t P,
                                       void* stream) {
   if (Bn == 0) return 0;
-  l2norm_scale_bwd_kernel<<<(Bn * 32 + 127) / 128, 128, 0, ST(stream)>>>(dy, x, inv_norm, scale, dx, dx_bf16, Bn, P);
+  l2norm_scale_bwd_kernel<<<(Bn * 32 + 127) / 128, 128, 0, ST(stream)>>>(dy, x, inv_norm, scale, dx, dx_bf16, Bn, P); note_launch();
   MISSM_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
@@ -428,7 +429,7 @@ extern "C" int missm_text_embed_fwd(const int64_t* ids, const int32_t* sample_in
   if (Bn == 0) return 0;
   MISSM_REQUIRE(D % 4 == 0, "text_embed: D=%d", D);
   text_embed_fwd_kernel<<<grid_for(static_cast<long>(Bn) * L * (D / 4), 256), 256, 0, ST(stream)>>>(
-      ids, sample_index, tok_emb, pos_emb, out, Bn, L, D);
+      ids, sample_index, tok_emb, pos_emb, out, Bn, L, D); note_launch();
   MISSM_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
@@ -437,14 +438,14 @@ extern "C" int missm_text_embed_bwd(const int64_t* ids, const int32_t* sample_in
                                     float* dtok_emb, float* dpos, int32_t Bn, int32_t L, int32_t D,
                                     void* stream) {
   text_embed_bwd_kernel<<<grid_for(static_cast<long>(L) * D, 128), 128, 0, ST(stream)>>>(
-      ids, sample_index, dx, dtok_emb, dpos, Bn, L, D);
+      ids, sample_index, dx, dtok_emb, dpos, Bn, L, D); note_launch();
   MISSM_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
 extern "C" int missm_argmax_rows(const int64_t* ids, const int32_t* sample_index, int32_t* out_rows,
                                  int32_t Bn, int32_t L, void* stream) {
   if (Bn == 0) return 0;
-  argmax_rows_kernel<<<(Bn + 127) / 128, 128, 0, ST(stream)>>>(ids, sample_index, out_rows, Bn, L);
+  argmax_rows_kernel<<<(Bn + 127) / 128, 128, 0, ST(stream)>>>(ids, sample_index, out_rows, Bn, L); note_launch();
   MISSM_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
@@ -453,7 +454,7 @@ extern "C" int missm_colsum_grouped_f32(const float* x, int32_t M, int32_t D, in
                                         float* out, void* stream) {
   MISSM_REQUIRE(period > 0 && div > 0, "colsum_grouped: period=%d div=%d", period, div);
   dim3 grid((D + 127) / 128, period);
-  colsum_grouped_kernel<<<grid, 128, 0, ST(stream)>>>(x, M, D, period, div, out);
+  colsum_grouped_kernel<<<grid, 128, 0, ST(stream)>>>(x, M, D, period, div, out); note_launch();
   MISSM_CHECK_CUDA(cudaGetLastError());
   return 0;
 }

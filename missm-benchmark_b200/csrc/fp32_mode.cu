@@ -248,7 +248,7 @@ extern "C" int missm_expand6_bf16(const float* src, int64_t ld_src, int32_t rows
   int grid = static_cast<int>((total + 255) / 256);
   if (grid > 32 * kNumSMs) grid = 32 * kNumSMs;
   expand6_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(src, ld_src, rows, cols, static_cast<__nv_bfloat16*>(dst),
-                                                                       ld_dst, cols_pad, which, stack_rows);
+                                                                       ld_dst, cols_pad, which, stack_rows); note_launch();
   MISSM_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
@@ -257,7 +257,7 @@ extern "C" int missm_gelu_f32_fwd(const float* u, float* a, int64_t n, void* str
   if (n == 0) return 0;
   int grid = static_cast<int>((n + 255) / 256);
   if (grid > 32 * kNumSMs) grid = 32 * kNumSMs;
-  gelu_f32_fwd_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(u, a, n);
+  gelu_f32_fwd_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(u, a, n); note_launch();
   MISSM_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
@@ -266,7 +266,7 @@ extern "C" int missm_gelu_f32_bwd(const float* d_a, const float* u, float* d_u, 
   if (n == 0) return 0;
   int grid = static_cast<int>((n + 255) / 256);
   if (grid > 32 * kNumSMs) grid = 32 * kNumSMs;
-  gelu_f32_bwd_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(d_a, u, d_u, n);
+  gelu_f32_bwd_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(d_a, u, d_u, n); note_launch();
   MISSM_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
@@ -277,7 +277,7 @@ extern "C" int missm_attention_f32_fwd(const missm_attn_args* a, void* stream) {
   AttnF32Params p;
   if (int rc = fill_f32_params(a, p)) return rc;
   dim3 grid((p.N + F32_WARPS - 1) / F32_WARPS, p.H, p.n_seq);
-  attn_f32_query_kernel<0><<<grid, F32_WARPS * 32, 0, static_cast<cudaStream_t>(stream)>>>(p);
+  attn_f32_query_kernel<0><<<grid, F32_WARPS * 32, 0, static_cast<cudaStream_t>(stream)>>>(p); note_launch();
   MISSM_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
@@ -288,8 +288,8 @@ extern "C" int missm_attention_f32_bwd(const missm_attn_args* a, void* stream) {
   AttnF32Params p;
   if (int rc = fill_f32_params(a, p)) return rc;
   dim3 grid((p.N + F32_WARPS - 1) / F32_WARPS, p.H, p.n_seq);
-  attn_f32_query_kernel<1><<<grid, F32_WARPS * 32, 0, static_cast<cudaStream_t>(stream)>>>(p);
-  attn_f32_key_kernel<<<grid, F32_WARPS * 32, 0, static_cast<cudaStream_t>(stream)>>>(p);
+  attn_f32_query_kernel<1><<<grid, F32_WARPS * 32, 0, static_cast<cudaStream_t>(stream)>>>(p); note_launch();
+  attn_f32_key_kernel<<<grid, F32_WARPS * 32, 0, static_cast<cudaStream_t>(stream)>>>(p); note_launch();
   MISSM_CHECK_CUDA(cudaGetLastError());
   return 0;
 }

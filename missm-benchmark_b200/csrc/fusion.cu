@@ -191,7 +191,7 @@ extern "C" int missm_fusion_sum_fwd(const missm_fusion_sum_args* a, void* stream
   const size_t smem = sizeof(float) * (a->P + a->Fd);
   MISSM_REQUIRE(smem <= 48 * 1024, "fusion_sum: P + Fd too large for shared memory");
   fusion_sum_fwd_kernel<<<a->B, kFusionThreads, smem, static_cast<cudaStream_t>(stream)>>>(
-      p, a->n_modal, a->missing_index, a->gamma, a->beta, a->pre, a->out, a->mean, a->rstd, a->P, a->Fd, a->eps);
+      p, a->n_modal, a->missing_index, a->gamma, a->beta, a->pre, a->out, a->mean, a->rstd, a->P, a->Fd, a->eps); note_launch();
   MISSM_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
@@ -208,14 +208,14 @@ extern "C" int missm_fusion_sum_bwd(const missm_fusion_sum_args* a, const float*
   float* dg_part = workspace + n;
   float* db_part = workspace + 2 * n;
   fusion_sum_bwd_norm_kernel<<<a->B, kFusionThreads, 0, st>>>(d_out, a->pre, a->mean, a->rstd, a->gamma, d_pre,
-                                                              dg_part, db_part, a->Fd);
-  reduce_rows_f32_kernel<<<(a->Fd + 127) / 128, 128, 0, st>>>(dg_part, a->B, a->Fd, d_gamma);
-  reduce_rows_f32_kernel<<<(a->Fd + 127) / 128, 128, 0, st>>>(db_part, a->B, a->Fd, d_beta);
+                                                              dg_part, db_part, a->Fd); note_launch();
+  reduce_rows_f32_kernel<<<(a->Fd + 127) / 128, 128, 0, st>>>(dg_part, a->B, a->Fd, d_gamma); note_launch();
+  reduce_rows_f32_kernel<<<(a->Fd + 127) / 128, 128, 0, st>>>(db_part, a->B, a->Fd, d_beta); note_launch();
   fusion_sum_bwd_emb_kernel<<<dim3(a->B, a->n_modal), kFusionThreads, sizeof(float) * a->Fd, st>>>(
-      p, a->missing_index, d_pre, a->P, a->Fd);
+      p, a->missing_index, d_pre, a->P, a->Fd); note_launch();
   MISSM_REQUIRE(sizeof(float) * a->B <= 48 * 1024, "fusion_sum: batch too large for shared memory");
   fusion_sum_bwd_w_kernel<<<dim3(a->Fd, a->n_modal), kFusionThreads, sizeof(float) * a->B, st>>>(
-      p, a->missing_index, d_pre, a->B, a->P, a->Fd);
+      p, a->missing_index, d_pre, a->B, a->P, a->Fd); note_launch();
   MISSM_CHECK_CUDA(cudaGetLastError());
   return 0;
 }

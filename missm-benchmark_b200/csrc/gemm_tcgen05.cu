@@ -19,6 +19,8 @@
 #include <cstring>
 
 #include <atomic>
+#include <mutex>
+#include <vector>
 
 #include "../../include/missm_b200.h"
 #include "gemm_common.cuh"
@@ -300,7 +302,7 @@ static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const Gem
                                           Cfg::SMEM_BYTES));
     configured = true;
   }
-  kern<<<grid, kGemmThreads, Cfg::SMEM_BYTES, stream>>>(tmA, tmB, p);
+  kern<<<grid, kGemmThreads, Cfg::SMEM_BYTES, stream>>>(tmA, tmB, p); note_launch();
   MISSM_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
@@ -335,6 +337,64 @@ int gemm_launch_2cta(const missm_gemm_args* a, GemmParams p, cudaStream_t stream
 }
 using namespace missm;
 
+// ---------------------------------------------------------------------------------------
+// measurement hooks: launch counter + CUDA events around every GEMM launch (bench.py's roofline leg)
+// ---------------------------------------------------------------------------------------
+static std::atomic<long long> g_launches{0};
+namespace missm {
+void note_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
+}
+namespace {
+struct GemmProfile {
+  std::mutex mu;
+  bool on = false;
+  std::vector<cudaEvent_t> ev;      // pairs
+  std::vector<double> flop;
+};
+GemmProfile g_prof;
+}  // namespace
+extern "C" int64_t missm_launch_count(int32_t reset) {
+  return reset ? g_launches.exchange(0, std::memory_order_relaxed) : g_launches.load(std::memory_order_relaxed);
+}
+extern "C" int missm_gemm_profile(int32_t on) {
+  std::lock_guard<std::mutex> lk(g_prof.mu);
+  if (on) {
+    for (cudaEvent_t e : g_prof.ev) cudaEventDestroy(e);
+    g_prof.ev.clear(), g_prof.flop.clear();
+  }
+  g_prof.on = on != 0;
+  return 0;
+}
+extern "C" int missm_gemm_profile_read(double* ms, double* flop, int64_t* launches) {
+  std::lock_guard<std::mutex> lk(g_prof.mu);
+  double t = 0.0, f = 0.0;
+  for (size_t i = 0; i + 1 < g_prof.ev.size(); i += 2) {
+    MISSM_CHECK_CUDA(cudaEventSynchronize(g_prof.ev[i + 1]));
+    float one = 0.f;
+    MISSM_CHECK_CUDA(cudaEventElapsedTime(&one, g_prof.ev[i], g_prof.ev[i + 1]));
+    t += one, f += g_prof.flop[i / 2];
+  }
+  if (ms) *ms = t;
+  if (flop) *flop = f;
+  if (launches) *launches = static_cast<int64_t>(g_prof.ev.size() / 2);
+  return 0;
+}
+static int gemm_bf16_impl(const missm_gemm_args* a, void* stream_v);
+extern "C" int missm_gemm_bf16(const missm_gemm_args* a, void* stream_v) {
+  if (!g_prof.on || a == nullptr || a->M <= 0) return gemm_bf16_impl(a, stream_v);
+  cudaEvent_t e0, e1;
+  MISSM_CHECK_CUDA(cudaEventCreate(&e0));
+  MISSM_CHECK_CUDA(cudaEventCreate(&e1));
+  cudaStream_t st = static_cast<cudaStream_t>(stream_v);
+  MISSM_CHECK_CUDA(cudaEventRecord(e0, st));
+  const int rc = gemm_bf16_impl(a, stream_v);
+  MISSM_CHECK_CUDA(cudaEventRecord(e1, st));
+  std::lock_guard<std::mutex> lk(g_prof.mu);
+  g_prof.ev.push_back(e0), g_prof.ev.push_back(e1);
+  g_prof.flop.push_back(2.0 * a->M * a->N * a->K);
+  return rc;
+}
+
 extern "C" int missm_version(void) { return MISSM_ABI_VERSION; }
 extern "C" const char* missm_last_error(void) { return g_last_error; }
 extern "C" int missm_set_persistent_sms(int32_t n) {
@@ -343,7 +403,7 @@ extern "C" int missm_set_persistent_sms(int32_t n) {
   return 0;
 }
 
-extern "C" int missm_gemm_bf16(const missm_gemm_args* a, void* stream_v) {
+static int gemm_bf16_impl(const missm_gemm_args* a, void* stream_v) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_v);
   MISSM_REQUIRE(a != nullptr, "null args");
   MISSM_REQUIRE(a->M >= 0 && a->N > 0 && a->K > 0, "bad dims M=%d N=%d K=%d", a->M, a->N, a->K);

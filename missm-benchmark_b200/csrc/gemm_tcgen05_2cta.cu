@@ -333,7 +333,7 @@ static int launch_gemm2_sched(const CUtensorMap& tmA, const CUtensorMap& tmB, co
     MISSM_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
     configured = true;
   }
-  kern<<<grid, kGemmThreads, Cfg::SMEM_BYTES, stream>>>(tmA, tmB, p);
+  kern<<<grid, kGemmThreads, Cfg::SMEM_BYTES, stream>>>(tmA, tmB, p); note_launch();
   MISSM_CHECK_CUDA(cudaGetLastError());
   return 0;
 }

@@ -290,7 +290,7 @@ static int launch_ln_fwd(int vec, int grid, cudaStream_t st, const float* x, lon
 #define LN_CASE(V)                                                                              \
   case V:                                                                                       \
     layernorm_fwd_kernel<V, OUT_BF16><<<grid, kLnWarps * 32, 0, st>>>(                          \
-        x, ldx, ridx, add_rows, add_period, add_div, x_out, g, b, y, ldy, mean, rstd, M, eps);  \
+        x, ldx, ridx, add_rows, add_period, add_div, x_out, g, b, y, ldy, mean, rstd, M, eps); note_launch();  \
     break;
   switch (vec) {
     LN_CASE(1) LN_CASE(2) LN_CASE(3) LN_CASE(4) LN_CASE(5) LN_CASE(6) LN_CASE(8) LN_CASE(10)
@@ -311,12 +311,12 @@ static int launch_ln_bwd(int vec, int grid, cudaStream_t st, const void* dy, lon
 #define LN_CASE(V)                                                                         \
   case V:                                                                                  \
     layernorm_bwd_kernel<V, DY_BF16><<<grid, kLnWarps * 32, 0, st>>>(                      \
-        dy, lddy, x, ldx, ridx, mean, rstd, gamma, dres, dx, dxb, partial, M);             \
+        dy, lddy, x, ldx, ridx, mean, rstd, gamma, dres, dx, dxb, partial, M); note_launch();             \
     break;
 #define LN2_CASE(V)                                                                        \
   case V:                                                                                  \
     layernorm_bwd2_kernel<V / 2, DY_BF16><<<grid, kLn2Warps * 32, 0, st>>>(                \
-        dy, lddy, x, ldx, ridx, mean, rstd, gamma, dres, dx, dxb, partial, M);             \
+        dy, lddy, x, ldx, ridx, mean, rstd, gamma, dres, dx, dxb, partial, M); note_launch();             \
     break;
   static const bool one_warp_rows = getenv("MISSM_LN_BWD_1WARP") != nullptr;   // A/B switch
   if ((vec == 6 || vec == 8) && !one_warp_rows) {
@@ -394,12 +394,12 @@ extern "C" int missm_layernorm_bwd(const void* dy, int64_t lddy, int32_t dy_bf16
   if (rc) return rc;
   if (dbeta == dgamma + D && (dx_colsum == nullptr || dx_colsum == dbeta + D)) {  // contiguous output: one launch
     const int n = (dx_colsum ? 3 : 2) * D;
-    reduce_partials_kernel<<<(n + 31) / 32, dim3(32, 8), 0, st>>>(partial, grid, 3L * D, dgamma, n, 1.f);
+    reduce_partials_kernel<<<(n + 31) / 32, dim3(32, 8), 0, st>>>(partial, grid, 3L * D, dgamma, n, 1.f); note_launch();
   } else {
-    reduce_partials_kernel<<<(D + 31) / 32, dim3(32, 8), 0, st>>>(partial, grid, 3L * D, dgamma, D, 1.f);
-    reduce_partials_kernel<<<(D + 31) / 32, dim3(32, 8), 0, st>>>(partial + D, grid, 3L * D, dbeta, D, 1.f);
+    reduce_partials_kernel<<<(D + 31) / 32, dim3(32, 8), 0, st>>>(partial, grid, 3L * D, dgamma, D, 1.f); note_launch();
+    reduce_partials_kernel<<<(D + 31) / 32, dim3(32, 8), 0, st>>>(partial + D, grid, 3L * D, dbeta, D, 1.f); note_launch();
     if (dx_colsum)
-      reduce_partials_kernel<<<(D + 31) / 32, dim3(32, 8), 0, st>>>(partial + 2 * D, grid, 3L * D, dx_colsum, D, 1.f);
+      reduce_partials_kernel<<<(D + 31) / 32, dim3(32, 8), 0, st>>>(partial + 2 * D, grid, 3L * D, dx_colsum, D, 1.f); note_launch();
   }
   MISSM_CHECK_CUDA(cudaGetLastError());
   return 0;
@@ -408,7 +408,7 @@ extern "C" int missm_layernorm_bwd(const void* dy, int64_t lddy, int32_t dy_bf16
 extern "C" int missm_reduce_partials(const float* partial, int32_t R, int64_t stride, float* out,
                                      int32_t n, float scale, void* stream) {
   reduce_partials_kernel<<<(n + 31) / 32, dim3(32, 8), 0, static_cast<cudaStream_t>(stream)>>>(
-      partial, R, stride, out, n, scale);
+      partial, R, stride, out, n, scale); note_launch();
   MISSM_CHECK_CUDA(cudaGetLastError());
   return 0;
 }

@@ -14,6 +14,8 @@ constexpr int kNumSMs = 148;  // B200: 2 dies x 74 SMs
 // parallelism MISSM_PERSISTENT_SMS (even, e.g. 132) leaves a few SMs to NCCL's all-reduce CTAs, which
 // cannot co-reside with one-CTA-per-SM kernels that own the whole register file and shared memory.
 int persistent_sms();
+// one call per kernel launch this library issues (missm_launch_count: bench.py's `gpu_launches`)
+void note_launch();
 
 // ----------------------------------------------------------------------------------------
 // error plumbing (host)

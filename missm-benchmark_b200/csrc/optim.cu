@@ -126,7 +126,7 @@ extern "C" int missm_adam_multi(const missm_adam_args* a, void* stream) {
       reinterpret_cast<float* const*>(a->params), reinterpret_cast<float* const*>(a->grads),
       reinterpret_cast<float* const*>(a->exp_avg), reinterpret_cast<float* const*>(a->exp_avg_sq),
       reinterpret_cast<__nv_bfloat16* const*>(a->bf16_out), a->numel, a->step_size, a->bc2_sqrt, a->chunk_tensor,
-      a->chunk_offset, a->n_chunks, static_cast<long>(a->chunk_elems), h, a->zero_grads);
+      a->chunk_offset, a->n_chunks, static_cast<long>(a->chunk_elems), h, a->zero_grads); note_launch();
   MISSM_CHECK_CUDA(cudaGetLastError());
   return 0;
 }

@@ -171,11 +171,11 @@ extern "C" int missm_image_preprocess(const missm_preproc_args* a, void* stream)
   if (a->src_f32) {
     if (smem > 48 * 1024)
       MISSM_CHECK_CUDA(cudaFuncSetAttribute(image_preprocess_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    image_preprocess_kernel<true><<<grid, kTile * kTile, smem, st>>>(p);
+    image_preprocess_kernel<true><<<grid, kTile * kTile, smem, st>>>(p); note_launch();
   } else {
     if (smem > 48 * 1024)
       MISSM_CHECK_CUDA(cudaFuncSetAttribute(image_preprocess_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    image_preprocess_kernel<false><<<grid, kTile * kTile, smem, st>>>(p);
+    image_preprocess_kernel<false><<<grid, kTile * kTile, smem, st>>>(p); note_launch();
   }
   MISSM_CHECK_CUDA(cudaGetLastError());
   return 0;

@@ -7,6 +7,8 @@ I = ctypes.c_int32
 L = ctypes.c_int64
 F = ctypes.c_float
 
+ABI_VERSION = 7          # == MISSM_ABI_VERSION of include/missm_b200.h; _lib.lib() refuses a library built for another
+
 # name -> argtypes (every function returns int32; 0 = ok)
 SIGNATURES = {
     "missm_gemm_bf16": [P, P],
@@ -45,6 +47,14 @@ SIGNATURES = {
     "missm_attention_f32_bwd": [P, P],
     "missm_adam_multi": [P, P],
     "missm_image_preprocess": [P, P],
+    "missm_attn_block_sizes": [P, P],
+    "missm_attn_block_fwd": [P, P],
+    "missm_attn_block_bwd": [P, P],
+    "missm_mlp_block_sizes": [P, P],
+    "missm_mlp_block_fwd": [P, P],
+    "missm_mlp_block_bwd": [P, P],
+    "missm_gemm_profile": [I],
+    "missm_gemm_profile_read": [P, P, P],
 }
 # exported but with non-standard return types / no args
-OTHER_EXPORTS = ["missm_version", "missm_last_error"]
+OTHER_EXPORTS = ["missm_version", "missm_last_error", "missm_launch_count"]

@@ -63,6 +63,14 @@ def lib():
     L = ctypes.CDLL(LIB_PATH)
     L.missm_version.restype = c_int
     L.missm_last_error.restype = ctypes.c_char_p
+    from . import _abi
+    if L.missm_version() != _abi.ABI_VERSION:
+        # a stale build would read the by-pointer argument structs with another layout: refuse it
+        raise RuntimeError(
+            f"missm_b200: {LIB_PATH} was built for ABI v{L.missm_version()} but this package binds ABI "
+            f"v{_abi.ABI_VERSION}. Rebuild it (`make -C missm-benchmark_b200/csrc` or __graft_entry__.build()).")
+    L.missm_launch_count.restype = ctypes.c_int64
+    L.missm_launch_count.argtypes = [c_int]
     _declare(L)
     _lib = L
     return L
@@ -76,7 +84,11 @@ def _declare(L):
         fn.argtypes = argtypes
 
 
+CALLS = [0]      # binding calls made so far (one check() per call): bench.py reports them per step
+
+
 def check(rc, what=""):
+    CALLS[0] += 1
     if rc != 0:
         msg = lib().missm_last_error().decode("utf-8", "replace")
         raise RuntimeError(f"missm_b200 {what} failed (rc={rc}): {msg}")

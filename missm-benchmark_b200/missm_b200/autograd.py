@@ -10,35 +10,40 @@ import os
 import torch
 from torch.utils.weak import WeakIdKeyDictionary
 
-from . import ops
+from . import blocks, ops
 from .ops import BF16, F32, EPI_DGELU, EPI_GELU, EPI_PATCH, EPI_RESID
 
 # ------------------------------------------------------------------------------------------
-# side channel: bf16 copy of a residual-stream gradient, produced by the LayerNorm-backward of
-# block k and consumed by block k-1 (autograd itself only carries the fp32 tensor)
+# side channel: the bf16 copy of a residual-stream gradient and its column sums (= the bias gradient of the Linear
+# that produced the stream), which the LayerNorm-backward of block k emits for free and block k-1 consumes.
+# autograd itself only carries the fp32 tensor, so the pair rides on that tensor OBJECT as an attribute (torch
+# preserves a tensor's Python object, attributes included, while the engine holds it) -- no process-global state,
+# nothing to reset, safe with several models / re-entrant backwards.  A gradient that was accumulated, copied or
+# modified on the way arrives without (or with a stale) attribute and the consumer recomputes what it needs.
 # ------------------------------------------------------------------------------------------
-_GRAD_BF16 = {}
+_AB_NO_LN_COLSUM = os.environ.get("MISSM_AB_NO_LN_COLSUM") is not None     # A/B measurement switch
 
 
-_AB_NO_LN_COLSUM = os.environ.get("MISSM_AB_NO_LN_COLSUM") is not None     # A/B measurement switches
-_AB_DGELU_COLSUM = os.environ.get("MISSM_AB_DGELU_COLSUM") is not None
-
-
-def _publish_bf16(grad_f32, grad_bf16, colsum=None):
+def _give_side(grad_f32, grad_bf16, colsum=None):
     if _AB_NO_LN_COLSUM:
         colsum = None
-    # holding grad_f32 keeps its storage alive, so a pointer match means "the same tensor"
-    _GRAD_BF16[grad_f32.data_ptr()] = (grad_f32, grad_bf16, colsum)
+    grad_f32._missm_side = (grad_bf16, colsum, grad_f32._version)
+
+
+def _take_side(grad_f32):
+    """-> (bf16 copy | None, column sums [D] | None) riding on this gradient tensor."""
+    hit = grad_f32.__dict__.pop("_missm_side", None)
+    if hit is not None and hit[2] == grad_f32._version and hit[0].shape == grad_f32.shape:
+        return hit[0], hit[1]
+    return None, None
 
 
 def _bf16_of(grad_f32):
-    """-> (bf16 copy, column sums [D]) of a residual-stream gradient; both come for free from the
-    LayerNorm-backward kernel that produced it, else they are computed here."""
-    hit = _GRAD_BF16.pop(grad_f32.data_ptr(), None)
-    if hit is not None and hit[0].shape == grad_f32.shape and hit[0]._version == grad_f32._version:
-        return hit[1], (hit[2] if hit[2] is not None else ops.colsum(hit[1]))
-    b = ops.cast_bf16(grad_f32)
-    return b, ops.colsum(b)
+    """-> (bf16 copy, column sums [D]) of a residual-stream gradient, from the side channel or computed here."""
+    b, cs = _take_side(grad_f32)
+    if b is None:
+        b = ops.cast_bf16(grad_f32)
+    return b, (cs if cs is not None else ops.colsum(b))
 
 
 # ------------------------------------------------------------------------------------------
@@ -60,10 +65,6 @@ def get_precision():
     if _PRECISION[0] not in ("bf16", "fp32"):
         raise ValueError(f"MISSM_PRECISION must be 'bf16' or 'fp32', got {_PRECISION[0]!r}")
     return _PRECISION[0]
-
-
-def reset_side_channel():
-    _GRAD_BF16.clear()
 
 
 def _contig(g):
@@ -181,73 +182,17 @@ class AttnMeta:
 
 
 # ------------------------------------------------------------------------------------------
-# x + OutProj(Attention(QKV(LN(x [+ temporal embedding]))))
-#   reference: CLIPEncoderLayer.forward, languagebind/image/modeling_image.py:105-127 (temporal)
-#   and :137-146 (spatial); CLIPAttention = transformers 4.3x
-# ------------------------------------------------------------------------------------------
-class AttnBlockFn(torch.autograd.Function):
-    @staticmethod
-    def forward(ctx, x, meta, cache, ln_w, ln_b, qw, qb, kw, kb, vw, vb, ow, ob, temb):
-        D = x.shape[1]
-        hd = D // meta.H
-        wqkv, bqkv = packed_qkv(cache, qw, kw, vw, qb, kb, vb)
-        wo = bf16_weight(cache, "o", ow)
-        if temb is not None:
-            # hidden_states + temporal_embedding[:, :t]  (modeling_image.py:110-114); out of place
-            x_res = torch.empty_like(x)
-            h, mean, rstd = ops.layernorm_fwd(x, ln_w, ln_b, meta.eps, add_rows=temb.detach().reshape(-1, D),
-                                              add_period=meta.add_period, add_div=meta.add_div, x_out=x_res)
-        else:
-            x_res = x
-            h, mean, rstd = ops.layernorm_fwd(x, ln_w, ln_b, meta.eps)
-        qkv = ops.gemm(h, wqkv, bias=bqkv, scale_cols=D, col_scale=hd ** -0.5)
-        attn, lse = ops.attention_fwd(qkv, meta.layout, meta.H, causal=meta.causal, key_mask=meta.key_mask,
-                                      mask_rows=meta.mask_rows, mask_div=meta.mask_div)
-        out = ops.gemm(attn, wo, bias=ob.detach(), epilogue=EPI_RESID, aux_in=x_res, out_dtype=F32)
-        ctx.meta = meta
-        ctx.has_temb = temb is not None
-        ctx.save_for_backward(x_res, mean, rstd, h, qkv, attn, lse, wqkv, wo, ln_w)
-        return out
-
-    @staticmethod
-    def backward(ctx, d_out):
-        x_res, mean, rstd, h, qkv, attn, lse, wqkv, wo, ln_w = ctx.saved_tensors
-        meta = ctx.meta
-        D = x_res.shape[1]
-        hd = D // meta.H
-        d_out = _contig(d_out)
-        d_out_b, d_ob = _bf16_of(d_out)
-        # a frozen encoder (peft freezes everything but the adapters, modeling_image.py:793) asks for no weight
-        # gradients: dgrad only
-        wgrads = any(ctx.needs_input_grad[5:13])
-        d_ow = ops.gemm(d_out_b, attn, a_mn=True, b_mn=True, out_dtype=F32) if wgrads else None   # dY^T @ attn
-        d_attn = ops.gemm(d_out_b, wo, b_mn=True)                                      # dY @ Wo
-        dqkv, d_bqkv = ops.attention_bwd(qkv, attn, lse, d_attn, meta.layout, meta.H, hd ** -0.5, causal=meta.causal,
-                                         key_mask=meta.key_mask, mask_rows=meta.mask_rows, mask_div=meta.mask_div,
-                                         want_colsum=wgrads)
-        d_wqkv = ops.gemm(dqkv, h, a_mn=True, b_mn=True, out_dtype=F32) if wgrads else None      # [3D, D]
-        d_h = ops.gemm(dqkv, wqkv, b_mn=True)
-        dx, dx_b, d_lnw, d_lnb, dx_cs = ops.layernorm_bwd(d_h, x_res, mean, rstd, ln_w, dres=d_out, want_bf16=True)
-        _publish_bf16(dx, dx_b, dx_cs)
-        d_temb = None
-        if ctx.has_temb:
-            d_temb = ops.colsum_grouped(dx, meta.add_period, meta.add_div).view(1, meta.add_period, D)
-        if not wgrads:
-            return (dx, None, None, d_lnw, d_lnb) + (None,) * 8 + (d_temb,)
-        return (dx, None, None, d_lnw, d_lnb, d_wqkv[:D], d_bqkv[:D], d_wqkv[D:2 * D], d_bqkv[D:2 * D],
-                d_wqkv[2 * D:], d_bqkv[2 * D:], d_ow, d_ob, d_temb)
-
-
-# ------------------------------------------------------------------------------------------
-# The same block with peft LoRA adapters on q / k / v / out_proj (reference: convert_to_lora,
-# modeling_image.py:775-793; peft's Linear: y = W x + b + (alpha / r) B(A(x))).
-#
-# Adapters ride on the tcgen05 GEMMs through the CONTRACTION dimension instead of being merged into W (a bf16
-# copy of W + sBA would round away a delta that is ~2^-8 of W early in training) or run as separate rank-r GEMM
-# chains: with T = X A_cat^T (one skinny GEMM, r_pad = 8 columns per group) stored NEXT to X in one row-major
-# buffer [X | T], the layer is ONE GEMM over K' = K + r_pad against [W | sB]; in the backward [dY | dY sB] against
-# the row-stacked [W ; A_cat] gives dX in ONE GEMM, and dA_cat = (dY sB)^T X, d(sB) = dY^T T are two skinny
-# wgrads.  Every operand is a column view of a wider-pitched buffer; nothing is copied or transposed.
+# One encoder layer = a chain of residual blocks, each issued by ONE driver call (blocks.py / csrc/blocks.cu):
+#   attention block  x + OutProj(Attention(QKV(LN(x [+ temporal embedding]))))
+#                    reference: CLIPEncoderLayer.forward, languagebind/image/modeling_image.py:105-127 (temporal)
+#                    and :137-146 (spatial); CLIPAttention = transformers 4.3x
+#   MLP block        x + fc2(quick_gelu(fc1(LN(x))))      modeling_image.py:129-134, :148-151; CLIPMLP
+# LoRA (peft Linear y = W x + b + (alpha / r) B(A(x)); reference convert_to_lora, modeling_image.py:775-793): the
+# adapters ride on the tcgen05 GEMMs through the CONTRACTION dimension instead of being merged into W (a bf16 copy
+# of W + sBA would round away a delta that is ~2^-8 of W early in training) or run as separate rank-r GEMM chains:
+# with T = X A_cat^T (one skinny GEMM, r_pad = 8 columns per group) stored NEXT to X in one row-major buffer
+# [X | T], the layer is ONE GEMM over K' = K + r_pad against [W | sB]; in the backward [dY | dY sB] against the
+# row-stacked [W ; A_cat] gives dX in ONE GEMM, and dA_cat = (dY sB)^T X, d(sB) = dY^T T are two skinny wgrads.
 # The encoder's own weights are frozen by peft, so their wgrads / bias sums are skipped (needs_input_grad).
 # ------------------------------------------------------------------------------------------
 def _pad8(n):
@@ -296,133 +241,92 @@ def lora_packs(cache, base, adapters, scaling):
     return packs
 
 
-class LoraAttnBlockFn(torch.autograd.Function):
+
+class BlockPlan:
+    """Static description of one residual block of a layer: kind, where its parameters sit in the flat parameter
+    tuple the Function receives, and the owning module's operand cache."""
+    __slots__ = ("kind", "cache", "n", "has_temb", "lora", "scaling", "eps", "which")
+
+    def __init__(self, kind, cache, has_temb=False, lora=False, scaling=1.0, eps=1e-5, which="spatial"):
+        self.kind, self.cache, self.has_temb, self.lora, self.scaling, self.eps = kind, cache, has_temb, lora, scaling, eps
+        self.which = which                     # attention: "spatial" or "temporal" (which AttnMeta applies)
+        # attn: ln_w ln_b qw qb kw kb vw vb ow ob [temb] [qA qB kA kB vA vB oA oB];  mlp: ln_w ln_b w1 b1 w2 b2
+        self.n = (10 + int(has_temb) + (8 if lora else 0)) if kind == "attn" else 6
+
+
+def attn_weights(blk, ps):
+    ln_w, ln_b, qw, qb, kw, kb, vw, vb, ow, ob = ps[:10]
+    temb = ps[10] if blk.has_temb else None
+    if blk.lora:
+        ad = ps[10 + int(blk.has_temb):]
+        wf_qkv, wb_qkv, wf_o, wb_o, bqkv = lora_packs(blk.cache, (qw, qb, kw, kb, vw, vb, ow, ob), ad, blk.scaling)
+        return blocks.AttnWeights(ln_w, ln_b, wf_qkv, bqkv, wf_o, ob, temb, ad[0].shape[0], wb_qkv, wb_o)
+    wqkv, bqkv = packed_qkv(blk.cache, qw, kw, vw, qb, kb, vb)
+    return blocks.AttnWeights(ln_w, ln_b, wqkv, bqkv, bf16_weight(blk.cache, "o", ow), ob, temb)
+
+
+def mlp_weights(blk, ps):
+    ln_w, ln_b, w1, b1, w2, b2 = ps
+    return blocks.MlpWeights(ln_w, ln_b, bf16_weight(blk.cache, "fc1", w1), b1, bf16_weight(blk.cache, "fc2", w2), b2)
+
+
+class EncoderLayerFn(torch.autograd.Function):
+    """x -> layer(x) for a chain of residual blocks (`plan`: tuple of BlockPlan; `metas`: {"spatial": AttnMeta,
+    "temporal": AttnMeta | None}); `params` = the blocks' parameters, flattened in plan order.  Returns an explicit
+    gradient for every parameter that asks for one (DDP at train_ddp.py:189 runs with find_unused_parameters=False)."""
+
     @staticmethod
-    def forward(ctx, x, meta, cache, ln_w, ln_b, qw, qb, kw, kb, vw, vb, ow, ob, temb,
-                qA, qB, kA, kB, vA, vB, oA, oB, scaling):
-        M, D = x.shape
-        hd = D // meta.H
-        r = qA.shape[0]
-        R3, R1 = _pad8(3 * r), _pad8(r)
-        wf_qkv, wb_qkv, wf_o, wb_o, bqkv = lora_packs(cache, (qw, qb, kw, kb, vw, vb, ow, ob),
-                                                      (qA, qB, kA, kB, vA, vB, oA, oB), scaling)
-        hcat = torch.empty((M, D + R3), device=x.device, dtype=BF16)        # [LN(x) | LN(x) A_cat^T]
-        h = hcat[:, :D]
-        if temb is not None:
-            x_res = torch.empty_like(x)
-            _, mean, rstd = ops.layernorm_fwd(x, ln_w, ln_b, meta.eps, add_rows=temb.detach().reshape(-1, D),
-                                              add_period=meta.add_period, add_div=meta.add_div, x_out=x_res, out=h)
-        else:
-            x_res = x
-            _, mean, rstd = ops.layernorm_fwd(x, ln_w, ln_b, meta.eps, out=h)
-        ops.gemm(h, wb_qkv[3 * D:], out=hcat[:, D:])                         # T = h A_cat^T          [M, R3]
-        qkvcat = torch.empty((M, 3 * D + R3), device=x.device, dtype=BF16)   # pitch shared with [dqkv | dT]
-        qkv = qkvcat[:, :3 * D]
-        ops.gemm(hcat, wf_qkv, bias=bqkv, scale_cols=D, col_scale=hd ** -0.5, out=qkv)
-        attncat = torch.empty((M, D + R1), device=x.device, dtype=BF16)      # [attn | attn A_o^T]
-        attn = attncat[:, :D]
-        _, lse = ops.attention_fwd(qkv, meta.layout, meta.H, causal=meta.causal, key_mask=meta.key_mask,
-                                   mask_rows=meta.mask_rows, mask_div=meta.mask_div, out=attn)
-        ops.gemm(attn, wb_o[D:], out=attncat[:, D:])
-        out = ops.gemm(attncat, wf_o, bias=ob.detach(), epilogue=EPI_RESID, aux_in=x_res, out_dtype=F32)
-        ctx.meta, ctx.has_temb, ctx.r, ctx.scaling = meta, temb is not None, r, scaling
-        ctx.save_for_backward(x_res, mean, rstd, hcat, qkvcat, attncat, lse, wf_qkv, wb_qkv, wf_o, wb_o, ln_w)
-        return out
+    def forward(ctx, x, plan, metas, *params):
+        states, cur, i = [], x, 0
+        for blk in plan:
+            ps = params[i:i + blk.n]
+            i += blk.n
+            if blk.kind == "attn":
+                cur, st = blocks.attn_fwd(metas[blk.which], cur, attn_weights(blk, ps))
+            else:
+                cur, st = blocks.mlp_fwd(blk.eps, cur, mlp_weights(blk, ps))
+            states.append(st)
+        states[0].keep = states[0].keep[:1]          # the layer input is kept by save_for_backward below
+        ctx.plan, ctx.states = plan, states
+        ctx.save_for_backward(x)
+        return cur
 
     @staticmethod
     def backward(ctx, d_out):
-        x_res, mean, rstd, hcat, qkvcat, attncat, lse, wf_qkv, wb_qkv, wf_o, wb_o, ln_w = ctx.saved_tensors
-        meta, r, s = ctx.meta, ctx.r, ctx.scaling
-        M, D = x_res.shape
-        hd = D // meta.H
-        R3, R1 = _pad8(3 * r), _pad8(r)
+        plan, states = ctx.plan, ctx.states
         need = ctx.needs_input_grad
-        base_grads = any(need[5:13])                       # somebody un-froze the encoder's own weights
-        h, qkv, attn = hcat[:, :D], qkvcat[:, :3 * D], attncat[:, :D]
-        d_out = _contig(d_out)
-        _GRAD_BF16.pop(d_out.data_ptr(), None)
-        # ---- out_proj group: [dY | dY sB_o] ----
-        dycat = ops.cast_bf16(d_out, cols_dst=D + R1)
-        dy = dycat[:, :D]
-        ops.gemm(dy, wf_o[:, D:], b_mn=True, out=dycat[:, D:])                               # dT_o = dY (sB_o)
-        d_attncat = torch.empty((M, D + R1), device=d_out.device, dtype=BF16)                # pitch of attn
-        d_attn = d_attncat[:, :D]
-        ops.gemm(dycat, wb_o, b_mn=True, out=d_attn)                                         # dY W_o + dT_o A_o
-        d_oA = ops.gemm(dycat[:, D:], attn, a_mn=True, b_mn=True, out_dtype=F32)[:r]         # dT_o^T attn
-        d_oB = ops.gemm(dy, attncat[:, D:], a_mn=True, b_mn=True, out_dtype=F32)[:, :r] * s  # dY^T T_o
-        d_ow = d_ob = None
-        if base_grads:
-            d_ow = ops.gemm(dy, attn, a_mn=True, b_mn=True, out_dtype=F32)
-            d_ob = ops.colsum(dy)
-        # ---- attention core ----
-        dqkvcat = torch.empty((M, 3 * D + R3), device=d_out.device, dtype=BF16)
-        dqkv = dqkvcat[:, :3 * D]
-        _, d_bqkv = ops.attention_bwd(qkv, attn, lse, d_attn, meta.layout, meta.H, hd ** -0.5, causal=meta.causal,
-                                      key_mask=meta.key_mask, mask_rows=meta.mask_rows, mask_div=meta.mask_div,
-                                      dqkv_out=dqkv, want_colsum=base_grads)
-        # ---- q / k / v group: [dqkv | dqkv sB_cat] ----
-        ops.gemm(dqkv, wf_qkv[:, D:], b_mn=True, out=dqkvcat[:, 3 * D:])                     # dT      [M, R3]
-        d_h = ops.gemm(dqkvcat, wb_qkv, b_mn=True)                                           # dqkv W + dT A_cat
-        d_acat = ops.gemm(dqkvcat[:, 3 * D:], h, a_mn=True, b_mn=True, out_dtype=F32)        # [R3, D]
-        d_sb = ops.gemm(dqkv, hcat[:, D:], a_mn=True, b_mn=True, out_dtype=F32)              # [3D, R3]
-        d_A = [d_acat[i * r:(i + 1) * r] for i in range(3)]
-        d_B = [d_sb[i * D:(i + 1) * D, i * r:(i + 1) * r] * s for i in range(3)]
-        d_w = [None] * 3
-        d_b = [None] * 3
-        if base_grads:
-            d_wqkv = ops.gemm(dqkv, h, a_mn=True, b_mn=True, out_dtype=F32)
-            d_w = [d_wqkv[i * D:(i + 1) * D] for i in range(3)]
-            d_b = [d_bqkv[i * D:(i + 1) * D] for i in range(3)]
-        dx, dx_b, d_lnw, d_lnb, dx_cs = ops.layernorm_bwd(d_h, x_res, mean, rstd, ln_w, dres=d_out, want_bf16=True)
-        _publish_bf16(dx, dx_b, dx_cs)
-        d_temb = None
-        if ctx.has_temb:
-            d_temb = ops.colsum_grouped(dx, meta.add_period, meta.add_div).view(1, meta.add_period, D)
-        return (dx, None, None, d_lnw, d_lnb, d_w[0], d_b[0], d_w[1], d_b[1], d_w[2], d_b[2], d_ow, d_ob, d_temb,
-                d_A[0], d_B[0], d_A[1], d_B[1], d_A[2], d_B[2], d_oA, d_oB, None)
-
-
-# ------------------------------------------------------------------------------------------
-# x + fc2(quick_gelu(fc1(LN(x))))      reference: modeling_image.py:129-134, :148-151; CLIPMLP
-# ------------------------------------------------------------------------------------------
-class MlpBlockFn(torch.autograd.Function):
-    @staticmethod
-    def forward(ctx, x, eps, cache, ln_w, ln_b, w1, b1, w2, b2):
-        w1b = bf16_weight(cache, "fc1", w1)
-        w2b = bf16_weight(cache, "fc2", w2)
-        h, mean, rstd = ops.layernorm_fwd(x, ln_w, ln_b, eps)
-        u = torch.empty((x.shape[0], w1.shape[0]), device=x.device, dtype=BF16)
-        a = ops.gemm(h, w1b, bias=b1.detach(), epilogue=EPI_GELU, aux_out=u)
-        out = ops.gemm(a, w2b, bias=b2.detach(), epilogue=EPI_RESID, aux_in=x, out_dtype=F32)
-        ctx.save_for_backward(x, mean, rstd, h, u, a, w1b, w2b, ln_w)
-        return out
-
-    @staticmethod
-    def backward(ctx, d_out):
-        x, mean, rstd, h, u, a, w1b, w2b, ln_w = ctx.saved_tensors
-        d_out = _contig(d_out)
-        d_out_b, d_b2 = _bf16_of(d_out)
-        if not any(ctx.needs_input_grad[5:9]):             # frozen MLP (peft-wrapped encoder): dgrad only
-            d_u = ops.gemm(d_out_b, w2b, b_mn=True, epilogue=EPI_DGELU, aux_in=u)
-            d_h = ops.gemm(d_u, w1b, b_mn=True)
-            dx, dx_b, d_lnw, d_lnb, dx_cs = ops.layernorm_bwd(d_h, x, mean, rstd, ln_w, dres=d_out, want_bf16=True)
-            _publish_bf16(dx, dx_b, dx_cs)
-            return dx, None, None, d_lnw, d_lnb, None, None, None, None
-        d_w2 = ops.gemm(d_out_b, a, a_mn=True, b_mn=True, out_dtype=F32)
-        if _AB_DGELU_COLSUM:
-            d_b1 = torch.zeros((u.shape[1],), device=u.device, dtype=F32)
-            d_u = ops.gemm(d_out_b, w2b, b_mn=True, epilogue=EPI_DGELU, aux_in=u, colsum_out=d_b1)
-        else:
-            d_u = ops.gemm(d_out_b, w2b, b_mn=True, epilogue=EPI_DGELU, aux_in=u)     # (dY @ W2) * gelu'(u)
-        d_w1 = ops.gemm(d_u, h, a_mn=True, b_mn=True, out_dtype=F32)
-        # (the GEMM can also emit this column sum -- colsum_out -- but the dGELU epilogue is already the
-        #  bound of that kernel: measured 3 ms / step slower than this separate HBM-bound pass)
-        if not _AB_DGELU_COLSUM:
-            d_b1 = ops.colsum(d_u)
-        d_h = ops.gemm(d_u, w1b, b_mn=True)
-        dx, dx_b, d_lnw, d_lnb, dx_cs = ops.layernorm_bwd(d_h, x, mean, rstd, ln_w, dres=d_out, want_bf16=True)
-        _publish_bf16(dx, dx_b, dx_cs)
-        return dx, None, None, d_lnw, d_lnb, d_w1, d_b1, d_w2, d_b2
+        d = _contig(d_out)
+        d_b, d_cs = _take_side(d)
+        out, i = [None] * (len(need) - 3), len(need) - 3
+        for blk, st in zip(reversed(plan), reversed(states)):
+            i -= blk.n
+            if blk.kind == "attn":
+                wgrad = any(need[3 + i + 2:3 + i + 10])
+                dx, dx_b, G = blocks.attn_bwd(st, d, d_b, d_cs is not None, wgrad)
+                D = dx.shape[1]
+                g = [G["ln_w"], G["ln_b"]] + [None] * 8
+                if wgrad:
+                    wq, bq = G["w_qkv"], G["b_qkv"]
+                    g[2:10] = [wq[:D], bq[:D], wq[D:2 * D], bq[D:2 * D], wq[2 * D:], bq[2 * D:], G["w_o"],
+                               d_cs if d_cs is not None else G["b_o"]]
+                if blk.has_temb:
+                    g.append(G["temb"].view(1, -1, D))
+                if blk.lora:
+                    r, s = st.w.lora_r, blk.scaling
+                    for k in range(3):
+                        g += [G["a_cat"][k * r:(k + 1) * r], G["sb_cat"][k * D:(k + 1) * D, k * r:(k + 1) * r] * s]
+                    g += [G["a_o"][:r], G["sb_o"][:, :r] * s]
+            else:
+                wgrad = any(need[3 + i + 2:3 + i + 6])
+                dx, dx_b, G = blocks.mlp_bwd(st, d, d_b, d_cs is not None, wgrad)
+                g = [G["ln_w"], G["ln_b"]] + [None] * 4
+                if wgrad:
+                    g[2:6] = [G["w1"], G["b1"], G["w2"], d_cs if d_cs is not None else G["b2"]]
+            out[i:i + blk.n] = g
+            d, d_b, d_cs = dx, dx_b, G["dx_colsum"]
+        ctx.states = None
+        _give_side(d, d_b, d_cs)
+        return (d, None, None, *out)
 
 
 # ------------------------------------------------------------------------------------------
@@ -454,7 +358,7 @@ class VisionEmbedFn(torch.autograd.Function):
         tok, mean, rstd, patches, ln_w = ctx.saved_tensors
         n_img, P, D, K, wshape = ctx.dims
         d_x0 = _contig(d_x0)
-        _GRAD_BF16.pop(d_x0.data_ptr(), None)
+        _take_side(d_x0)
         d_tok, _, d_lnw, d_lnb, _ = ops.layernorm_bwd(d_x0, tok, mean, rstd, ln_w)
         d_pos, d_patch = ops.embed_bwd(d_tok, n_img, P + 1)
         d_w = ops.gemm(d_patch, patches, a_mn=True, b_mn=True, out_dtype=F32)          # [D, Kpad]
@@ -481,7 +385,7 @@ class TextEmbedFn(torch.autograd.Function):
         ids, present_idx = ctx.saved_tensors
         n_present, vocab, n_pos, has_idx = ctx.info
         d_x0 = _contig(d_x0)
-        _GRAD_BF16.pop(d_x0.data_ptr(), None)
+        _take_side(d_x0)
         d_tok, d_pos_used = ops.text_embed_bwd(ids, d_x0, vocab, sample_index=present_idx if has_idx else None,
                                                n_samples=n_present)
         if d_pos_used.shape[0] != n_pos:
@@ -529,7 +433,7 @@ class PoolProjFn(torch.autograd.Function):
         dx_b = torch.zeros(x.shape, device=x.device, dtype=BF16)
         _, _, d_lnw, d_lnb, dx_cs = ops.layernorm_bwd(d_pooled, x, mean, rstd, ln_w, row_index=rows, dx=dx,
                                                        dx_bf16=dx_b)
-        _publish_bf16(dx, dx_b, dx_cs)
+        _give_side(dx, dx_b, dx_cs)
         return dx, None, None, None, None, None, None, d_lnw, d_lnb, d_proj
 
 
@@ -575,25 +479,32 @@ def _pick(bf16_fn, f32_name):
     return bf16_fn
 
 
-def attn_block(*args):
-    return _pick(AttnBlockFn, "AttnBlockF32Fn").apply(*args)
-
-
-def lora_attn_block(x, meta, cache, ln_w, ln_b, qw, qb, kw, kb, vw, vb, ow, ob, temb,
-                    qA, qB, kA, kB, vA, vB, oA, oB, scaling):
-    if get_precision() == "fp32":
-        # verification mode: the adapter folded into an effective fp32 weight W + s B A (exact in fp32; torch
-        # autograd carries dW_eff back to A and B -- [D, r] parameter-space products, not a performance path)
-        from . import autograd_f32
-        eff = [w + scaling * (B @ A) for w, A, B in ((qw, qA, qB), (kw, kA, kB), (vw, vA, vB), (ow, oA, oB))]
-        return autograd_f32.AttnBlockF32Fn.apply(x, meta, {}, ln_w, ln_b, eff[0], qb, eff[1], kb, eff[2], vb,
-                                                 eff[3], ob, temb)
-    return LoraAttnBlockFn.apply(x, meta, cache, ln_w, ln_b, qw, qb, kw, kb, vw, vb, ow, ob, temb,
-                                 qA, qB, kA, kB, vA, vB, oA, oB, scaling)
-
-
-def mlp_block(*args):
-    return _pick(MlpBlockFn, "MlpBlockF32Fn").apply(*args)
+def encoder_layer(x, plan, metas, params):
+    """One CLIPEncoderLayer over the fp32 residual stream x [M, D].  bf16 mode: ONE autograd node whose forward /
+    backward issue one driver call per residual block; fp32 verification mode: the per-block fp32 Functions."""
+    if get_precision() != "fp32":
+        return EncoderLayerFn.apply(x, plan, metas, *params)
+    from . import autograd_f32
+    i = 0
+    for blk in plan:
+        ps = params[i:i + blk.n]
+        i += blk.n
+        if blk.kind == "mlp":
+            x = autograd_f32.MlpBlockF32Fn.apply(x, blk.eps, blk.cache, *ps)
+            continue
+        meta = metas[blk.which]
+        base, temb = ps[:10], (ps[10] if blk.has_temb else None)
+        if blk.lora:
+            # verification mode: the adapter folded into an effective fp32 weight W + s B A (exact in fp32; torch
+            # autograd carries dW_eff back to A and B -- [D, r] parameter-space products, not a performance path)
+            ln_w, ln_b, qw, qb, kw, kb, vw, vb, ow, ob = base
+            qA, qB, kA, kB, vA, vB, oA, oB = ps[10 + int(blk.has_temb):]
+            eff = [w + blk.scaling * (B @ A) for w, A, B in ((qw, qA, qB), (kw, kA, kB), (vw, vA, vB), (ow, oA, oB))]
+            x = autograd_f32.AttnBlockF32Fn.apply(x, meta, {}, ln_w, ln_b, eff[0], qb, eff[1], kb, eff[2], vb,
+                                                  eff[3], ob, temb)
+        else:
+            x = autograd_f32.AttnBlockF32Fn.apply(x, meta, blk.cache, *base, temb)
+    return x
 
 
 def vision_embed(*args):

@@ -133,7 +133,6 @@ class LanguageBind(nn.Module):
         """inputs: {modal: {'pixel_values': ...} | {'input_ids', 'attention_mask'}} -> {modal: [B, P]}.
         `missing_index` (int64 [B], optional) enables compaction: a tower only runs the samples whose
         code differs from its own; rows of missing samples come back as zeros."""
-        ag.reset_side_channel()
         ddp_sms = _ddp_backward_sms() if torch.is_grad_enabled() else 0
         if ddp_sms:
             ops.set_persistent_sms(0)          # forward: no all-reduce in flight, all SMs

@@ -47,8 +47,6 @@ class _MaskedSumNorm(torch.autograd.Function):
         mean = torch.empty((B,), device=dev, dtype=F32)
         rstd = torch.empty((B,), device=dev, dtype=F32)
         a = _fill(embs, ws, bs, codes, mi, gamma.detach(), beta.detach(), pre, out, mean, rstd, eps)
-        from . import ops as _ops
-        _ops.LAUNCHES[0] += 1
         check(lib().missm_fusion_sum_fwd(ctypes.byref(a), stream_ptr()), "fusion_sum_fwd")
         ctx.n, ctx.codes, ctx.eps = n, codes, eps
         ctx.save_for_backward(mi, gamma, beta, pre, mean, rstd, *embs, *ws, *bs)
@@ -71,8 +69,6 @@ class _MaskedSumNorm(torch.autograd.Function):
         d_gamma = torch.empty((Fd,), device=dev, dtype=F32)
         d_beta = torch.empty((Fd,), device=dev, dtype=F32)
         d_out = d_out.contiguous()
-        from . import ops as _ops
-        _ops.LAUNCHES[0] += 5
         check(lib().missm_fusion_sum_bwd(ctypes.byref(a), ctypes.c_void_p(d_out.data_ptr()),
                                          ctypes.c_void_p(work.data_ptr()), ctypes.c_void_p(d_gamma.data_ptr()),
                                          ctypes.c_void_p(d_beta.data_ptr()), stream_ptr()), "fusion_sum_bwd")

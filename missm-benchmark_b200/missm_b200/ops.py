@@ -14,10 +14,8 @@ from ._lib import AttnArgs, GemmArgs, check, lib, stream_ptr
 EPI_LINEAR, EPI_GELU, EPI_RESID, EPI_DGELU, EPI_PATCH = range(5)
 BF16, F32 = torch.bfloat16, torch.float32
 
-# bookkeeping for bench.py: number of OUR kernels launched, and (optionally) CUDA-event pairs
-# around every GEMM launch on the launching stream: list of (start, end, flop)
-LAUNCHES = [0]
-GEMM_TIMING = None
+# (bench.py's bookkeeping -- kernels launched, CUDA events around every GEMM -- lives in the library itself:
+#  missm_launch_count / missm_gemm_profile, so that launches issued by the block drivers are seen too)
 
 
 def set_persistent_sms(n):
@@ -68,14 +66,6 @@ def gemm(a, b, *, a_mn=False, b_mn=False, out=None, out_dtype=BF16, bias=None,
     if colsum_out is not None:
         assert colsum_out.dtype == F32 and colsum_out.numel() == N and colsum_out.is_contiguous()
         g.colsum_out = colsum_out.data_ptr()
-    LAUNCHES[0] += 1
-    if GEMM_TIMING is not None and M > 0:
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        check(lib().missm_gemm_bf16(ctypes.byref(g), stream_ptr()), "gemm_bf16")
-        e1.record()
-        GEMM_TIMING.append((e0, e1, 2.0 * M * N * K))
-        return out
     check(lib().missm_gemm_bf16(ctypes.byref(g), stream_ptr()), "gemm_bf16")
     return out
 
@@ -128,7 +118,6 @@ def attention_fwd(qkv, lay, H, *, causal=False, key_mask=None, mask_rows=None, m
     assert out.dtype == BF16 and out.shape == (qkv.shape[0], D)
     lse = torch.empty((lay.n_seq, H, lay.N), device=qkv.device, dtype=F32)
     a = _attn_args(qkv, out, lse, lay, H, causal, key_mask, mask_rows, mask_div)
-    LAUNCHES[0] += 1
     check(lib().missm_attention_fwd(ctypes.byref(a), stream_ptr()), "attention_fwd")
     return out, lse
 
@@ -150,7 +139,6 @@ def attention_bwd(qkv, out, lse, d_out, lay, H, q_scale, *, causal=False, key_ma
     a.d_out, a.delta, a.dqkv, a.q_scale = d_out.data_ptr(), delta.data_ptr(), dqkv.data_ptr(), q_scale
     csum = None
     a.colsum_done = 0
-    LAUNCHES[0] += 3
     check(lib().missm_attention_bwd(ctypes.byref(a), stream_ptr()), "attention_bwd")
     if want_colsum and not a.colsum_done:
         csum = colsum(dqkv)
@@ -172,7 +160,6 @@ def layernorm_fwd(x, gamma, beta, eps, *, out_dtype=BF16, row_index=None, n_rows
         y = torch.empty((M, D), device=x.device, dtype=out_dtype)
     mean = torch.empty((M,), device=x.device, dtype=F32) if want_stats else None
     rstd = torch.empty((M,), device=x.device, dtype=F32) if want_stats else None
-    LAUNCHES[0] += 1
     check(lib().missm_layernorm_fwd(_p(x), _ld(x), _p(row_index), _p(add_rows), add_period, add_div,
                                     _p(x_out if x_out is not None else x) if add_rows is not None else None,
                                     _p(gamma), _p(beta),
@@ -197,7 +184,6 @@ def layernorm_bwd(dy, x, mean, rstd, gamma, *, dres=None, row_index=None, dx=Non
     partial = torch.empty((nparts, 3, D), device=x.device, dtype=F32)
     dgb = torch.empty((3, D), device=x.device, dtype=F32)
     dgamma, dbeta, dcol = dgb[0], dgb[1], dgb[2]
-    LAUNCHES[0] += 2
     check(lib().missm_layernorm_bwd(_p(dy), _ld(dy), int(dy.dtype == BF16), _p(x), _ld(x),
                                     _p(row_index), _p(mean), _p(rstd), _p(gamma), _p(dres), _p(dx),
                                     _p(dx_bf16), _p(partial), _p(dgamma), _p(dbeta), _p(dcol), M, D,
@@ -213,7 +199,6 @@ def cast_bf16(src, out=None, cols_dst=None):
     cols_dst = cols if cols_dst is None else cols_dst
     if out is None:
         out = torch.empty((rows, cols_dst), device=src.device, dtype=BF16)
-    LAUNCHES[0] += 1
     check(lib().missm_cast_f32_bf16(_p(src), _ld(src), _p(out), _ld(out), rows, cols, cols_dst,
                                     stream_ptr()), "cast_f32_bf16")
     return out
@@ -226,7 +211,6 @@ def colsum(x):
     R = lib().missm_colsum_num_partials(M)
     partial = torch.empty((R, N), device=x.device, dtype=F32)
     out = torch.empty((N,), device=x.device, dtype=F32)
-    LAUNCHES[0] += 2
     check(lib().missm_colsum_bf16(_p(x), _ld(x), M, N, _p(partial), _p(out), stream_ptr()), "colsum")
     return out
 
@@ -239,7 +223,6 @@ def patchify(pixels, ps, Kpad, T=1, sample_index=None, n_samples=None):
     C, H, W = pixels.shape[1], pixels.shape[-2], pixels.shape[-1]
     Bn = n_samples if n_samples is not None else pixels.shape[0]
     out = torch.empty((Bn * T * (H // ps) * (W // ps), Kpad), device=pixels.device, dtype=BF16)
-    LAUNCHES[0] += 2
     check(lib().missm_patchify(_p(pixels), _p(sample_index), _p(out), Bn, C, T, H, W, ps, Kpad,
                                stream_ptr()), "patchify")
     return out
@@ -250,7 +233,6 @@ def colsum_grouped(x, period, div):
     assert x.dtype == F32 and x.is_contiguous()
     M, D = x.shape
     out = torch.empty((period, D), device=x.device, dtype=F32)
-    LAUNCHES[0] += 1
     check(lib().missm_colsum_grouped_f32(_p(x), M, D, period, div, _p(out), stream_ptr()), "colsum_grouped")
     return out
 
@@ -263,7 +245,6 @@ def copy_f32(src, dst):
 
 
 def cls_rows(cls, pos, tok, Bn, ntok):
-    LAUNCHES[0] += 1
     check(lib().missm_cls_rows(_p(cls), _p(pos), _p(tok), Bn, ntok, tok.shape[1], stream_ptr()), "cls_rows")
 
 
@@ -271,7 +252,6 @@ def embed_bwd(dtok, Bn, ntok):
     D = dtok.shape[1]
     dpos = torch.empty((ntok, D), device=dtok.device, dtype=F32)
     dpatch = torch.empty((Bn * (ntok - 1), D), device=dtok.device, dtype=BF16)
-    LAUNCHES[0] += 1
     check(lib().missm_embed_bwd(_p(dtok), _p(dpos), _p(dpatch), Bn, ntok, D, stream_ptr()), "embed_bwd")
     return dpos, dpatch
 
@@ -279,7 +259,6 @@ def embed_bwd(dtok, Bn, ntok):
 def frame_mean(x, Bn, T, out_dtype=BF16):
     D = x.shape[1]
     out = torch.empty((Bn, D), device=x.device, dtype=out_dtype)
-    LAUNCHES[0] += 1
     check(lib().missm_frame_mean(_p(x), _p(out), int(out_dtype == BF16), Bn, T, D, stream_ptr()), "frame_mean")
     return out
 
@@ -287,7 +266,6 @@ def frame_mean(x, Bn, T, out_dtype=BF16):
 def frame_mean_bwd(dout, Bn, T):
     D = dout.shape[1]
     din = torch.empty((Bn * T, D), device=dout.device, dtype=F32)
-    LAUNCHES[0] += 1
     check(lib().missm_frame_mean_bwd(_p(dout), _p(din), Bn, T, D, stream_ptr()), "frame_mean_bwd")
     return din
 
@@ -296,7 +274,6 @@ def l2norm_scale_fwd(x, scale):
     Bn, P = x.shape
     y = torch.empty_like(x)
     inv = torch.empty((Bn,), device=x.device, dtype=F32)
-    LAUNCHES[0] += 1
     check(lib().missm_l2norm_scale_fwd(_p(x), _p(y), _p(inv), scale, Bn, P, stream_ptr()), "l2norm_fwd")
     return y, inv
 
@@ -304,7 +281,6 @@ def l2norm_scale_fwd(x, scale):
 def l2norm_scale_bwd(dy, x, inv, scale, out_dtype=BF16):
     Bn, P = x.shape
     dx = torch.empty((Bn, P), device=x.device, dtype=out_dtype)
-    LAUNCHES[0] += 1
     check(lib().missm_l2norm_scale_bwd(_p(dy), _p(x), _p(inv), scale, _p(dx), int(out_dtype == BF16),
                                        Bn, P, stream_ptr()), "l2norm_bwd")
     return dx
@@ -316,7 +292,6 @@ def text_embed_fwd(ids, tok_emb, pos_emb, sample_index=None, n_samples=None):
     Bn = n_samples if n_samples is not None else ids.shape[0]
     D = tok_emb.shape[1]
     out = torch.empty((Bn * L, D), device=ids.device, dtype=F32)
-    LAUNCHES[0] += 1
     check(lib().missm_text_embed_fwd(_p(ids), _p(sample_index), _p(tok_emb), _p(pos_emb), _p(out), Bn,
                                      L, D, stream_ptr()), "text_embed_fwd")
     return out
@@ -328,7 +303,6 @@ def text_embed_bwd(ids, dx, vocab, sample_index=None, n_samples=None):
     D = dx.shape[1]
     dtok = torch.zeros((vocab, D), device=dx.device, dtype=F32)
     dpos = torch.empty((L, D), device=dx.device, dtype=F32)
-    LAUNCHES[0] += 1
     check(lib().missm_text_embed_bwd(_p(ids), _p(sample_index), _p(dx), _p(dtok), _p(dpos), Bn, L, D,
                                      stream_ptr()), "text_embed_bwd")
     return dtok, dpos
@@ -338,7 +312,6 @@ def argmax_rows(ids, sample_index=None, n_samples=None):
     L = ids.shape[1]
     Bn = n_samples if n_samples is not None else ids.shape[0]
     out = torch.empty((Bn,), device=ids.device, dtype=torch.int32)
-    LAUNCHES[0] += 1
     check(lib().missm_argmax_rows(_p(ids), _p(sample_index), _p(out), Bn, L, stream_ptr()), "argmax_rows")
     return out
 
@@ -354,7 +327,6 @@ def compact_mask(missing_index, codes):
     slot = torch.empty((T, B), device=dev, dtype=torch.int32)
     counts = torch.empty((T,), device=dev, dtype=torch.int32)
     codes_host = (ctypes.c_int32 * T)(*[int(c) for c in codes])
-    LAUNCHES[0] += 1
     check(lib().missm_compact_mask(_p(missing_index), B, ctypes.cast(codes_host, ctypes.c_void_p), T,
                                    _p(idx), _p(slot), _p(counts), stream_ptr()), "compact_mask")
     return idx, slot, counts
@@ -363,7 +335,6 @@ def compact_mask(missing_index, codes):
 def scatter_rows_zero(src, slot_of, B):
     P = src.shape[1]
     dst = torch.empty((B, P), device=slot_of.device, dtype=F32)
-    LAUNCHES[0] += 1
     check(lib().missm_scatter_rows_zero(_p(src), _p(slot_of), _p(dst), B, P, stream_ptr()), "scatter_rows_zero")
     return dst
 
@@ -373,7 +344,6 @@ def gather_rows(src, idx, n_rows):
     assert src.is_contiguous()
     row_bytes = src.stride(0) * src.element_size()
     dst = torch.empty((n_rows,) + tuple(src.shape[1:]), device=src.device, dtype=src.dtype)
-    LAUNCHES[0] += 1
     check(lib().missm_gather_rows(_p(src), _p(idx), _p(dst), n_rows, row_bytes, stream_ptr()), "gather_rows")
     return dst
 
@@ -402,7 +372,6 @@ def image_preprocess(src, out, S, mean, std, *, antialias, pre_div=255.0, clip_l
     a.H, a.W, a.S, a.antialias = src.shape[0], src.shape[1], S, int(bool(antialias))
     a.pre_div, a.clip_lo, a.clip_hi, a.post_div = pre_div, clip_lo, clip_hi, post_div
     a.mean, a.std_ = (ctypes.c_float * 3)(*mean), (ctypes.c_float * 3)(*std)
-    LAUNCHES[0] += 1
     check(lib().missm_image_preprocess(ctypes.byref(a), stream_ptr()), "image_preprocess")
     return out
 
@@ -417,7 +386,6 @@ def expand6(x, which, stack_rows, cols_pad=None):
     R, C = x.shape
     cp = C if cols_pad is None else cols_pad
     out = torch.empty((6 * R, C) if stack_rows else (R, 6 * cp), device=x.device, dtype=BF16)
-    LAUNCHES[0] += 1
     check(lib().missm_expand6_bf16(_p(x), _ld(x), R, C, _p(out), _ld(out), cp, which, int(stack_rows), stream_ptr()),
           "expand6_bf16")
     return out
@@ -443,7 +411,6 @@ def gemm_f32(a, b, *, a_mn=False, b_mn=False, out=None, bias=None, epilogue=EPI_
 def gelu_f32_fwd(u):
     assert u.dtype == F32 and u.is_contiguous()
     a = torch.empty_like(u)
-    LAUNCHES[0] += 1
     check(lib().missm_gelu_f32_fwd(_p(u), _p(a), u.numel(), stream_ptr()), "gelu_f32_fwd")
     return a
 
@@ -451,7 +418,6 @@ def gelu_f32_fwd(u):
 def gelu_f32_bwd(d_a, u):
     assert d_a.dtype == F32 and u.dtype == F32 and d_a.is_contiguous() and u.is_contiguous()
     d_u = torch.empty_like(u)
-    LAUNCHES[0] += 1
     check(lib().missm_gelu_f32_bwd(_p(d_a), _p(u), _p(d_u), u.numel(), stream_ptr()), "gelu_f32_bwd")
     return d_u
 
@@ -463,7 +429,6 @@ def attention_f32_fwd(qkv, lay, H, *, causal=False, key_mask=None, mask_rows=Non
     out = torch.empty((qkv.shape[0], D), device=qkv.device, dtype=F32)
     lse = torch.empty((lay.n_seq, H, lay.N), device=qkv.device, dtype=F32)
     a = _attn_args(qkv, out, lse, lay, H, causal, key_mask, mask_rows, mask_div)
-    LAUNCHES[0] += 1
     check(lib().missm_attention_f32_fwd(ctypes.byref(a), stream_ptr()), "attention_f32_fwd")
     return out, lse
 
@@ -476,7 +441,6 @@ def attention_f32_bwd(qkv, out, lse, d_out, lay, H, q_scale, *, causal=False, ke
     delta = torch.empty_like(lse)
     a = _attn_args(qkv, out, lse, lay, H, causal, key_mask, mask_rows, mask_div)
     a.d_out, a.delta, a.dqkv, a.q_scale = d_out.data_ptr(), delta.data_ptr(), dqkv.data_ptr(), q_scale
-    LAUNCHES[0] += 2
     check(lib().missm_attention_f32_bwd(ctypes.byref(a), stream_ptr()), "attention_f32_bwd")
     return dqkv
 
@@ -487,7 +451,6 @@ def patchify_f32(pixels, ps, Kpad, T=1, sample_index=None, n_samples=None):
     C, H, W = pixels.shape[1], pixels.shape[-2], pixels.shape[-1]
     Bn = n_samples if n_samples is not None else pixels.shape[0]
     out = torch.zeros((Bn * T * (H // ps) * (W // ps), Kpad), device=pixels.device, dtype=F32)
-    LAUNCHES[0] += 1
     check(lib().missm_patchify_f32(_p(pixels), _p(sample_index), _p(out), Bn, C, T, H, W, ps, Kpad, stream_ptr()),
           "patchify_f32")
     return out

@@ -173,7 +173,6 @@ class FusedAdam(torch.optim.Optimizer):
     def _launch(self, a, tab):
         with torch.cuda.device(tab['dev']):
             check(lib().missm_adam_multi(ctypes.byref(a), stream_ptr()), "adam_multi")
-        ops.LAUNCHES[0] += 1
         self.launches += 1
 
     # -------------------------------------------------------------------------------------- step

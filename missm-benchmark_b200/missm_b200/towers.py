@@ -159,33 +159,56 @@ class CLIPEncoderLayer(nn.Module):
         self._cache = {"sa": {}, "mlp": {}, "ta": {}, "tmlp": {}}
 
     @staticmethod
-    def _attn_params(ln, a):
-        return (ln.weight, ln.bias, a.q_proj.weight, a.q_proj.bias, a.k_proj.weight, a.k_proj.bias,
-                a.v_proj.weight, a.v_proj.bias, a.out_proj.weight, a.out_proj.bias)
-
-    def _attn(self, x, meta, cache, ln, a, temb):
+    def _attn_params(ln, a, temb=None):
+        ps = [ln.weight, ln.bias, a.q_proj.weight, a.q_proj.bias, a.k_proj.weight, a.k_proj.bias,
+              a.v_proj.weight, a.v_proj.bias, a.out_proj.weight, a.out_proj.bias]
+        if temb is not None:
+            ps.append(temb)
         if a.has_lora:
-            if a.q_proj.p_drop != 0.0 and self.training:
-                raise NotImplementedError("lora_dropout != 0 in training mode is not built (reference default 0.0, "
-                                          "configuration_image.py:202)")
-            return ag.lora_attn_block(x, meta, cache, *self._attn_params(ln, a), temb, *a.lora_params())
-        return ag.attn_block(x, meta, cache, *self._attn_params(ln, a), temb)
+            ps += a.lora_params()[:-1]
+        return ps
+
+    @staticmethod
+    def _mlp_params(ln, m):
+        return [ln.weight, ln.bias, m.fc1.weight, m.fc1.bias, m.fc2.weight, m.fc2.bias]
+
+    def _plan(self):
+        """The layer as a chain of residual blocks (static) + its parameters in plan order."""
+        hit = self.__dict__.get('_plan_cache')
+        if hit is None:
+            blocks, params = [], []
+
+            def attn(which, cache, ln, a, temb):
+                blocks.append(ag.BlockPlan("attn", cache, has_temb=temb is not None, lora=a.has_lora,
+                                           scaling=a.q_proj.scaling if a.has_lora else 1.0, which=which))
+                params.extend(self._attn_params(ln, a, temb))
+
+            def mlp(cache, ln, m):
+                blocks.append(ag.BlockPlan("mlp", cache, eps=self.eps))
+                params.extend(self._mlp_params(ln, m))
+
+            if self.add_time_attn:      # modeling_image.py:105-134 (video: no temporal MLP, modeling_video.py:235-240)
+                attn("temporal", self._cache["ta"], self.temporal_layer_norm1, self.temporal_attn,
+                     self.temporal_embedding if self.t != 1 else None)
+                if self.has_temporal_mlp:
+                    mlp(self._cache["tmlp"], self.temporal_layer_norm2, self.temporal_mlp)
+            attn("spatial", self._cache["sa"], self.layer_norm1, self.self_attn, None)      # :137-146
+            mlp(self._cache["mlp"], self.layer_norm2, self.mlp)                             # :148-151
+            hit = self.__dict__['_plan_cache'] = (tuple(blocks), tuple(params))
+        return hit
+
+    def _apply(self, fn, *args, **kwargs):
+        self.__dict__.pop('_plan_cache', None)         # .to() / .cuda() may replace parameter objects
+        return super()._apply(fn, *args, **kwargs)
 
     def run(self, x, spatial_meta, temporal_meta):
         """x: fp32 [M, D] residual stream, rows ordered (image, token)."""
-        if self.add_time_attn:
-            temb = self.temporal_embedding if self.t != 1 else None
-            x = self._attn(x, temporal_meta, self._cache["ta"], self.temporal_layer_norm1, self.temporal_attn, temb)
-            if self.has_temporal_mlp:
-                m = self.temporal_mlp
-                x = ag.mlp_block(x, self.eps, self._cache["tmlp"], self.temporal_layer_norm2.weight,
-                                        self.temporal_layer_norm2.bias, m.fc1.weight, m.fc1.bias,
-                                        m.fc2.weight, m.fc2.bias)
-        x = self._attn(x, spatial_meta, self._cache["sa"], self.layer_norm1, self.self_attn, None)
-        m = self.mlp
-        x = ag.mlp_block(x, self.eps, self._cache["mlp"], self.layer_norm2.weight, self.layer_norm2.bias,
-                                m.fc1.weight, m.fc1.bias, m.fc2.weight, m.fc2.bias)
-        return x
+        plan, params = self._plan()
+        for a in (self.self_attn, getattr(self, 'temporal_attn', None)):
+            if a is not None and a.has_lora and a.q_proj.p_drop != 0.0 and self.training:
+                raise NotImplementedError("lora_dropout != 0 in training mode is not built (reference default 0.0, "
+                                          "configuration_image.py:202)")
+        return ag.encoder_layer(x, plan, {"spatial": spatial_meta, "temporal": temporal_meta}, params)
 
 
 class CLIPEncoder(nn.Module):

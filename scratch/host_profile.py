@@ -24,7 +24,7 @@ ap.add_argument("--steps", type=int, default=3)
 ap.add_argument("--lora-r", type=int, default=0)
 a = ap.parse_args()
 
-from missm_b200 import _lib, bank, fusion_ops, ops, towers  # noqa: E402
+from missm_b200 import _lib, bank, blocks, fusion_ops, ops, towers  # noqa: E402
 import missm_b200.autograd as ag  # noqa: E402
 
 
@@ -34,6 +34,14 @@ class _Noop:
             return lambda M: 8
         if name == "missm_colsum_num_partials":
             return lambda M: 8
+        if name in ("missm_attn_block_sizes", "missm_mlp_block_sizes"):
+            def sizes(args, out):
+                a = args._obj
+                n = a.M * a.D
+                out[0], out[1] = 64 * n, 64 * n
+                out[2] = (4 * a.D * a.D + 16 * a.D) if name.startswith("missm_attn") else (2 * a.D * a.F + 8 * a.D + a.F)
+                return 0
+            return sizes
         return lambda *args: 0
 
 
@@ -41,7 +49,11 @@ noop = _Noop()
 _lib._lib = noop
 _lib.lib = lambda: noop
 ops.lib = lambda: noop
+blocks.lib = lambda: noop
+blocks.stream_ptr = lambda: None
 fusion_ops.lib = lambda: noop
+blocks.lib = lambda: noop
+blocks.stream_ptr = lambda: None
 ops.stream_ptr = lambda: None
 fusion_ops.stream_ptr = lambda: None
 
@@ -99,7 +111,7 @@ for _ in range(a.steps):
     step()
 dt = (time.perf_counter() - t0) / a.steps
 print(f"host issue time per step: {dt * 1e3:.1f} ms  (layers {a.layers}, B {B}, lora_r {a.lora_r}, "
-      f"{ops.LAUNCHES[0] // (a.steps + 1)} counted launches)")
+      f"{_lib.CALLS[0] // (a.steps + 1)} binding calls)")
 if a.profile:
     pr = cProfile.Profile()
     pr.enable()

@@ -389,6 +389,120 @@ def image_preprocess(src, out, S, mean, std, *, antialias, pre_div=255.0, clip_l
     return out
 
 
+
+# ------------------------------------------------------------------ residual-block drivers (csrc/blocks.cu)
+# Stand-ins for missm_attn_block_* / missm_mlp_block_*, composed from the op stand-ins above in the order the
+# header documents.  `state` is opaque to the product's autograd code; here it simply holds the saved tensors.
+class _EmuState:
+    def __init__(self, **kw):
+        self.__dict__.update(kw)
+        self.keep = (None,)
+
+
+def _pad8(n):
+    return (n + 7) // 8 * 8
+
+
+def block_attn_fwd(meta, x, w):
+    M, D = x.shape
+    r = w.lora_r
+    R3, R1 = (_pad8(3 * r), _pad8(r)) if r else (0, 0)
+    hcat = torch.zeros((M, D + R3), dtype=BF16)
+    if w.temb is not None:
+        x_res = torch.empty_like(x)
+        _, mean, rstd = layernorm_fwd(x, w.ln_w, w.ln_b, meta.eps, add_rows=w.temb.detach().reshape(-1, D),
+                                      add_period=meta.add_period, add_div=meta.add_div, x_out=x_res, out=hcat[:, :D],
+                                      out_dtype=BF16)
+    else:
+        x_res = x
+        _, mean, rstd = layernorm_fwd(x, w.ln_w, w.ln_b, meta.eps, out=hcat[:, :D], out_dtype=BF16)
+    if r:
+        gemm(hcat[:, :D], w.wb_qkv[3 * D:], out=hcat[:, D:])
+    qkvcat = torch.zeros((M, 3 * D + R3), dtype=BF16)
+    gemm(hcat, w.w_qkv[:, :D + R3], bias=w.b_qkv, scale_cols=D, col_scale=0.125, out=qkvcat[:, :3 * D])
+    attncat = torch.zeros((M, D + R1), dtype=BF16)
+    _, lse = attention_fwd(qkvcat[:, :3 * D], meta.layout, meta.H, causal=meta.causal, key_mask=meta.key_mask,
+                           mask_rows=meta.mask_rows, mask_div=meta.mask_div, out=attncat[:, :D])
+    if r:
+        gemm(attncat[:, :D], w.wb_o[D:], out=attncat[:, D:])
+    out = gemm(attncat, w.w_o[:, :D + R1], bias=w.b_o.detach(), epilogue=EPI_RESID, aux_in=x_res, out_dtype=F32)
+    return out, _EmuState(meta=meta, w=w, x_res=x_res, mean=mean, rstd=rstd, hcat=hcat, qkvcat=qkvcat, attncat=attncat,
+                          lse=lse, R3=R3, R1=R1)
+
+
+def block_attn_bwd(st, d_out, d_out_bf16, colsum_given, wgrad):
+    meta, w, R3, R1 = st.meta, st.w, st.R3, st.R1
+    M, D = d_out.shape
+    r = w.lora_r
+    h, qkv, attn = st.hcat[:, :D], st.qkvcat[:, :3 * D], st.attncat[:, :D]
+    G = {}
+    dycat = torch.zeros((M, D + R1), dtype=BF16)
+    dycat[:, :D] = d_out_bf16 if d_out_bf16 is not None else d_out.to(BF16)
+    dy = dycat[:, :D]
+    if wgrad and not colsum_given:
+        G["b_o"] = colsum(dy)
+    d_attncat = torch.zeros((M, D + R1), dtype=BF16)
+    if r:
+        gemm(dy, w.w_o[:, D:D + R1], b_mn=True, out=dycat[:, D:])
+        gemm(dycat, w.wb_o, b_mn=True, out=d_attncat[:, :D])
+        G["a_o"] = gemm(dycat[:, D:], attn, a_mn=True, b_mn=True, out_dtype=F32)
+        G["sb_o"] = gemm(dy, st.attncat[:, D:], a_mn=True, b_mn=True, out_dtype=F32)
+    else:
+        gemm(dy, w.w_o, b_mn=True, out=d_attncat[:, :D])
+    if wgrad:
+        G["w_o"] = gemm(dy, attn, a_mn=True, b_mn=True, out_dtype=F32)
+    dqkvcat = torch.zeros((M, 3 * D + R3), dtype=BF16)
+    dqkv = dqkvcat[:, :3 * D]
+    _, cs = attention_bwd(qkv, attn, st.lse, d_attncat[:, :D], meta.layout, meta.H, 0.125, causal=meta.causal,
+                          key_mask=meta.key_mask, mask_rows=meta.mask_rows, mask_div=meta.mask_div, dqkv_out=dqkv,
+                          want_colsum=wgrad)
+    if wgrad:
+        G["b_qkv"] = cs
+    if r:
+        gemm(dqkv, w.w_qkv[:, D:D + R3], b_mn=True, out=dqkvcat[:, 3 * D:])
+        d_h = gemm(dqkvcat, w.wb_qkv, b_mn=True)
+        G["a_cat"] = gemm(dqkvcat[:, 3 * D:], h, a_mn=True, b_mn=True, out_dtype=F32)
+        G["sb_cat"] = gemm(dqkv, st.hcat[:, D:], a_mn=True, b_mn=True, out_dtype=F32)
+    else:
+        d_h = gemm(dqkv, w.w_qkv, b_mn=True)
+    if wgrad:
+        G["w_qkv"] = gemm(dqkv, h, a_mn=True, b_mn=True, out_dtype=F32)
+    dx, dx_b, G["ln_w"], G["ln_b"], G["dx_colsum"] = layernorm_bwd(d_h, st.x_res, st.mean, st.rstd, w.ln_w, dres=d_out,
+                                                                   want_bf16=True)
+    if w.temb is not None:
+        G["temb"] = colsum_grouped(dx, meta.add_period, meta.add_div)
+    return dx, dx_b, G
+
+
+def block_mlp_fwd(eps, x, w):
+    h, mean, rstd = layernorm_fwd(x, w.ln_w, w.ln_b, eps, out_dtype=BF16)
+    u = torch.empty((x.shape[0], w.w1.shape[0]), dtype=BF16)
+    a = gemm(h, w.w1, bias=w.b1.detach(), epilogue=EPI_GELU, aux_out=u)
+    out = gemm(a, w.w2, bias=w.b2.detach(), epilogue=EPI_RESID, aux_in=x, out_dtype=F32)
+    return out, _EmuState(w=w, x=x, mean=mean, rstd=rstd, h=h, u=u, a=a)
+
+
+def block_mlp_bwd(st, d_out, d_out_bf16, colsum_given, wgrad):
+    w = st.w
+    dy = d_out_bf16 if d_out_bf16 is not None else d_out.to(BF16)
+    G = {}
+    if wgrad and not colsum_given:
+        G["b2"] = colsum(dy)
+    if wgrad:
+        G["w2"] = gemm(dy, st.a, a_mn=True, b_mn=True, out_dtype=F32)
+    d_u = gemm(dy, w.w2, b_mn=True, epilogue=EPI_DGELU, aux_in=st.u)
+    if wgrad:
+        G["w1"] = gemm(d_u, st.h, a_mn=True, b_mn=True, out_dtype=F32)
+        G["b1"] = colsum(d_u)
+    d_h = gemm(d_u, w.w1, b_mn=True)
+    dx, dx_b, G["ln_w"], G["ln_b"], G["dx_colsum"] = layernorm_bwd(d_h, st.x, st.mean, st.rstd, w.ln_w, dres=d_out,
+                                                                   want_bf16=True)
+    return dx, dx_b, G
+
+
+BLOCK_DRIVERS = {"attn_fwd": block_attn_fwd, "attn_bwd": block_attn_bwd, "mlp_fwd": block_mlp_fwd,
+                 "mlp_bwd": block_mlp_bwd}
+
 BF16_MODE_OPS = ["attention_fwd", "attention_bwd", "cast_bf16", "colsum", "patchify"]
 
 EMULATED_OPS = ["gemm", "expand6", "attention_f32_fwd", "attention_f32_bwd", "layernorm_fwd", "layernorm_bwd",
@@ -404,17 +518,20 @@ def emulated_fp32_mode(precision="fp32", wide_bf16=False):
     precision="bf16" exercises the PRODUCT blocks of autograd.py instead; with wide_bf16 every "bf16" buffer is
     really fp32 (the dtype constant is swapped), which isolates the host algebra -- operand views, pitches,
     gradient formulas -- from bf16 rounding."""
-    from missm_b200 import autograd as ag, bank, fusion_ops, ops, towers
+    from missm_b200 import autograd as ag, bank, blocks, fusion_ops, ops, towers
     here = globals()
     global BF16
     names = EMULATED_OPS + (BF16_MODE_OPS if precision == "bf16" else [])
     saved = {n: getattr(ops, n) for n in names}
     saved_dt = (BF16, ag.BF16, ops.BF16)
+    saved_drivers = {n: getattr(blocks, n) for n in BLOCK_DRIVERS}
     if wide_bf16:
         BF16 = ag.BF16 = ops.BF16 = torch.float32
     saved_guard, saved_bank_guard, saved_fusion = towers._require_cuda, bank._require_cuda_index, fusion_ops.masked_sum_norm
     for n in names:
         setattr(ops, n, here[n])
+    for n, f in BLOCK_DRIVERS.items():
+        setattr(blocks, n, f)
     towers._require_cuda = lambda t, what: None
     bank._require_cuda_index = lambda mi, mdev: mi
     fusion_ops.masked_sum_norm = masked_sum_norm
@@ -426,4 +543,6 @@ def emulated_fp32_mode(precision="fp32", wide_bf16=False):
         BF16, ag.BF16, ops.BF16 = saved_dt
         for n, f in saved.items():
             setattr(ops, n, f)
+        for n, f in saved_drivers.items():
+            setattr(blocks, n, f)
         towers._require_cuda, bank._require_cuda_index, fusion_ops.masked_sum_norm = saved_guard, saved_bank_guard, saved_fusion

@@ -16,7 +16,7 @@ def declared_functions():
     src = open(HEADER).read()
     src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
     out = {}
-    for m in re.finditer(r"\b(?:int|const char\*)\s+(missm_\w+)\s*\(([^;{]*?)\)\s*;", src, flags=re.S):
+    for m in re.finditer(r"\b(?:int|int64_t|const char\*)\s+(missm_\w+)\s*\(([^;{]*?)\)\s*;", src, flags=re.S):
         args = m.group(2).strip()
         n = 0 if args in ("", "void") else len([a for a in args.split(",") if a.strip()])
         out[m.group(1)] = n
@@ -64,7 +64,9 @@ def test_ctypes_table_matches_header(built):
 def test_library_loads_and_reports_version(built):
     from missm_b200 import _lib
     L = _lib.lib()
-    assert L.missm_version() == 6
+    from missm_b200 import _abi
+    hdr = int(re.search(r"#define\s+MISSM_ABI_VERSION\s+(\d+)", open(HEADER).read()).group(1))
+    assert L.missm_version() == hdr == _abi.ABI_VERSION
     assert isinstance(L.missm_last_error(), bytes)
 
 
@@ -74,10 +76,12 @@ def test_struct_mirrors_have_the_header_sizes(built):
     from missm_b200.fusion_ops import FusionSumArgs
     from missm_b200.optim import AdamArgs
     from missm_b200.ops import PreprocArgs
+    from missm_b200.blocks import AttnBlockArgs, MlpBlockArgs
     prog = r'''
 #include <stdio.h>
+#include <stddef.h>
 #include "missm_b200.h"
-int main(void) { printf("%zu %zu %zu %zu %zu\n", sizeof(missm_gemm_args), sizeof(missm_attn_args), sizeof(missm_fusion_sum_args), sizeof(missm_adam_args), sizeof(missm_preproc_args)); return 0; }
+int main(void) { printf("%zu %zu %zu %zu %zu %zu %zu %zu %zu %zu %zu\n", sizeof(missm_gemm_args), sizeof(missm_attn_args), sizeof(missm_fusion_sum_args), sizeof(missm_adam_args), sizeof(missm_preproc_args), sizeof(missm_attn_block_args), sizeof(missm_mlp_block_args), offsetof(missm_attn_block_args, x), offsetof(missm_attn_block_args, scratch), offsetof(missm_mlp_block_args, x), offsetof(missm_mlp_block_args, scratch)); return 0; }
 '''
     import tempfile
     with tempfile.TemporaryDirectory() as d:
@@ -87,4 +91,6 @@ int main(void) { printf("%zu %zu %zu %zu %zu\n", sizeof(missm_gemm_args), sizeof
         subprocess.run(["gcc", "-I", os.path.join(ROOT, "include"), c, "-o", exe], check=True)
         sizes = [int(x) for x in subprocess.run([exe], capture_output=True, text=True, check=True).stdout.split()]
     assert sizes == [ctypes.sizeof(GemmArgs), ctypes.sizeof(AttnArgs), ctypes.sizeof(FusionSumArgs),
-                     ctypes.sizeof(AdamArgs), ctypes.sizeof(PreprocArgs)]
+                     ctypes.sizeof(AdamArgs), ctypes.sizeof(PreprocArgs), ctypes.sizeof(AttnBlockArgs),
+                     ctypes.sizeof(MlpBlockArgs), AttnBlockArgs.x.offset, AttnBlockArgs.scratch.offset,
+                     MlpBlockArgs.x.offset, MlpBlockArgs.scratch.offset]
