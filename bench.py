@@ -262,10 +262,14 @@ def run_gpu_arm(a):
         barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
+        from missm_b200 import bank as _bank
+        w0 = _bank.HOST_WAIT_S[0]
         h0 = time.perf_counter()
         for _ in range(steps):
             fn()
-        host_ms[0] = (time.perf_counter() - h0) * 1e3 / steps      # time the host needs to ISSUE a step
+        # time the host needs to ISSUE a step = wall time of the loop minus the time it sat in the compaction
+        # read-back waiting for the GPU to drain the previous step
+        host_ms[0] = (time.perf_counter() - h0 - (_bank.HOST_WAIT_S[0] - w0)) * 1e3 / steps
         e1.record()
         barrier()
         ms = torch.tensor([e0.elapsed_time(e1)], device=dev)

@@ -316,7 +316,8 @@ int missm_image_preprocess(const missm_preproc_args* args, void* stream);
  *   w_qkv bf16 [3D, ldw_qkv] = q | k | v rows, b_qkv f32 [3D]; w_o bf16 [D, ldw_o], b_o f32 [D]; the q block of the
  *   projection is scaled by head_dim^-0.5 in the GEMM epilogue; sequence layout / masks as missm_attn_args.
  *   LoRA (lora_r > 0; peft Linear y = W x + b + s B(A x), reference convert_to_lora, modeling_image.py:775-793), with
- *   R3 = pad8(3 r), R1 = pad8(r): w_qkv = [W | s B_cat] (ldw_qkv >= D + R3), wb_qkv bf16 [3D + R3, D] = [W ; A_cat]
+ *   R3 = pad64(3 r), R1 = pad64(r) (rank groups padded with zeros to one 64-element K block of the GEMM tiles, so
+ *   that the contraction dimension D + R stays a multiple of the tile depth and no TMA box is out of bounds): w_qkv = [W | s B_cat] (ldw_qkv >= D + R3), wb_qkv bf16 [3D + R3, D] = [W ; A_cat]
  *   row-stacked; w_o = [W_o | s B_o] (ldw_o >= D + R1), wb_o bf16 [D + R1, D] = [W_o ; A_o].
  *   grads (floats, in this order): d_ln_w [D], d_ln_b [D], dx_colsum [D], d_w_qkv [3D, D], d_b_qkv [3D],
  *   d_w_o [D, D], d_b_o [D], d_add_rows [add_period, D] (if add_rows), then with LoRA d_A_cat [R3, D],
@@ -398,6 +399,10 @@ int missm_mlp_block_bwd(const missm_mlp_block_args* args, void* stream);
  * recorded events and returns the summed milliseconds, 2*M*N*K flops and launch count.
  * ------------------------------------------------------------------------------------- */
 int64_t missm_launch_count(int32_t reset);
+/* debugging aid (MISSM_DEBUG_EVENTS=1 records a CUDA event after every kernel-level call of the block drivers):
+ * prints, per stream, the first recorded call that has not finished -- what a stalled GPU is stuck on */
+int missm_debug_dump(void);
+int missm_debug_crumb(const char* label_static, void* stream);   /* record one more event (label must stay alive) */
 int missm_gemm_profile(int32_t on);
 int missm_gemm_profile_read(double* ms, double* flop, int64_t* launches);
 

@@ -524,7 +524,7 @@ int attention_bwd_tc(const missm_attn_args* a, cudaStream_t stream);  // attenti
 extern "C" int missm_attention_fwd(const missm_attn_args* a, void* stream) {
   if (a->n_seq == 0) return 0;
   // tcgen05 path for the shapes it covers (spatial ViT attention); general shapes below
-  static const bool legacy_only = getenv("MISSM_ATTN_LEGACY") != nullptr;
+  static const bool legacy_only = getenv("MISSM_ATTN_LEGACY") != nullptr || getenv("MISSM_ATTN_LEGACY_FWD") != nullptr;
   if (!legacy_only) {
     MISSM_REQUIRE(a->qkv && a->out, "attention_fwd: null tensor");
     const int rc = attention_fwd_tc(a, static_cast<cudaStream_t>(stream));
@@ -549,7 +549,7 @@ extern "C" int missm_attention_bwd(missm_attn_args* a, void* stream) {
   const long total = static_cast<long>(p.n_seq) * p.H * p.N;
   int dgrid = static_cast<int>((total + 255) / 256);
   if (dgrid > 16 * kNumSMs) dgrid = 16 * kNumSMs;
-  static const bool legacy_only = getenv("MISSM_ATTN_LEGACY") != nullptr;
+  static const bool legacy_only = getenv("MISSM_ATTN_LEGACY") != nullptr || getenv("MISSM_ATTN_LEGACY_BWD") != nullptr;
   if (!legacy_only) {
     const int rc = attention_bwd_tc(a, st);   // tcgen05 path for the shapes it covers (computes delta itself)
     if (rc >= 0) return rc;

@@ -20,6 +20,7 @@
 // Bound: MUFU (one ex2 per score) + TMEM read bandwidth.  Work per item = 4 * N^2 * 64 flop.
 #include <cstdlib>
 
+#define MISSM_KERNEL_TAG "attn_fwd_tc"
 #include "../../include/missm_b200.h"
 #include "attention_tail.cuh"
 #include "missm_common.cuh"

@@ -24,6 +24,7 @@
 // (together the usual "2.5 x forward" counts 10) x N^2 x 64 flop.
 #include <cstdlib>
 
+#define MISSM_KERNEL_TAG "attn_bwd_tc"
 #include "../../include/missm_b200.h"
 #include "attention_tail.cuh"
 #include "missm_common.cuh"

@@ -9,7 +9,10 @@
 //
 // Memory layout of `saved` / `scratch` / `grads`: see the *_layout structs below; every sub-buffer is 256-byte
 // aligned (TMA base addresses need 16).
+#include <cstdlib>
 #include <cstring>
+#include <mutex>
+#include <vector>
 
 #include "../../include/missm_b200.h"
 #include "missm_common.cuh"
@@ -20,7 +23,7 @@ namespace {
 
 constexpr int64_t kAlign = 256;
 inline int64_t up(int64_t v) { return (v + kAlign - 1) / kAlign * kAlign; }
-inline int pad8(int n) { return (n + 7) / 8 * 8; }
+inline int pad8(int n) { return (n + 63) / 64 * 64; }   // LoRA rank groups: padded to one 64-element K block
 
 struct Carver {
   char* base;
@@ -144,15 +147,30 @@ void fill_attn(missm_attn_args& t, const missm_attn_block_args* a, const bf16* q
   t.n_seq = a->n_seq, t.s_in = a->s_in, t.causal = a->causal, t.mask_div = a->mask_div;
 }
 
-#define RC(expr)                 \
-  do {                           \
-    if (int _rc = (expr)) return _rc; \
+// ---- debugging aid (MISSM_DEBUG_EVENTS=1): a CUDA event after every kernel-level call of a driver, so that a
+// stalled GPU can be asked which call never finished (missm_debug_dump; used by scratch/hang_watch.py)
+struct Crumb { cudaEvent_t ev; const char* what; void* stream; int line; };
+std::mutex g_crumb_mu;
+std::vector<Crumb> g_crumbs;
+const bool g_debug_events = getenv("MISSM_DEBUG_EVENTS") != nullptr;
+void crumb(const char* what, int line, void* stream) {
+  Crumb c{nullptr, what, stream, line};
+  cudaEventCreateWithFlags(&c.ev, cudaEventDisableTiming);
+  cudaEventRecord(c.ev, static_cast<cudaStream_t>(stream));
+  std::lock_guard<std::mutex> lk(g_crumb_mu);
+  g_crumbs.push_back(c);
+}
+
+#define RC(expr)                                            \
+  do {                                                      \
+    if (int _rc = (expr)) return _rc;                       \
+    if (g_debug_events) crumb(#expr, __LINE__, stream);     \
   } while (0)
 
 }  // namespace
 
 extern "C" int missm_attn_block_sizes(const missm_attn_block_args* a, int64_t sizes[3]) {
-  RC(check_attn(a));
+  if (int rc = check_attn(a)) return rc;
   sizes[0] = attn_saved(a, nullptr).bytes;
   sizes[1] = attn_scratch(a, nullptr).bytes;
   sizes[2] = attn_grads(a, nullptr).floats;
@@ -187,7 +205,6 @@ extern "C" int missm_attn_block_bwd(const missm_attn_block_args* a, void* stream
   RC(check_attn(a));
   MISSM_REQUIRE(a->saved && a->scratch && a->grads && a->d_out && a->dx && a->dx_bf16 && a->w_qkv && a->w_o && a->ln_w,
                 "attn_block_bwd: null pointer");
-  MISSM_REQUIRE(a->add_rows == nullptr || a->x != nullptr || true, "unreachable");
   const int M = a->M, D = a->D, R3 = r3_of(a), R1 = r1_of(a);
   const AttnSaved s = attn_saved(a, a->saved);
   const AttnScratch w = attn_scratch(a, a->scratch);
@@ -201,14 +218,8 @@ extern "C" int missm_attn_block_bwd(const missm_attn_block_args* a, void* stream
   const bf16* dy = static_cast<const bf16*>(a->d_out_bf16);
   int ld_dy = D;
   if (dy == nullptr || R1) {
-    // LoRA needs dY inside the pitched [dY | dT_o] buffer
-    if (dy == nullptr) {
-      RC(missm_cast_f32_bf16(a->d_out, D, w.dycat, ld_at, M, D, D, stream));
-    } else {
-      MISSM_CHECK_CUDA(cudaMemcpy2DAsync(w.dycat, static_cast<size_t>(ld_at) * 2, dy, static_cast<size_t>(D) * 2,
-                                         static_cast<size_t>(D) * 2, M, cudaMemcpyDeviceToDevice,
-                                         static_cast<cudaStream_t>(stream)));
-    }
+    // LoRA needs dY inside the pitched [dY | dT_o] buffer: one cast pass from the fp32 gradient either way
+    RC(missm_cast_f32_bf16(a->d_out, D, w.dycat, ld_at, M, D, D, stream));
     dy = w.dycat, ld_dy = ld_at;
   }
   if (wg && !a->d_out_colsum_given) RC(missm_colsum_bf16(dy, ld_dy, M, D, w.cs_part, g.b_o, stream));
@@ -304,7 +315,7 @@ int check_mlp(const missm_mlp_block_args* a) {
 }  // namespace
 
 extern "C" int missm_mlp_block_sizes(const missm_mlp_block_args* a, int64_t sizes[3]) {
-  RC(check_mlp(a));
+  if (int rc = check_mlp(a)) return rc;
   sizes[0] = mlp_saved(a, nullptr).bytes;
   sizes[1] = mlp_scratch(a, nullptr).bytes;
   sizes[2] = mlp_grads(a, nullptr).floats;
@@ -346,5 +357,32 @@ extern "C" int missm_mlp_block_bwd(const missm_mlp_block_args* a, void* stream) 
   RC(gemm(w.d_u, F, false, a->w1, D, true, w.d_h, D, false, M, D, F, stream));                              // d_u W1
   RC(missm_layernorm_bwd(w.d_h, D, 1, a->x, D, nullptr, s.mean, s.rstd, a->ln_w, a->d_out, a->dx, a->dx_bf16, w.ln_part, g.ln_w,
                          g.ln_b, g.dx_colsum, M, D, stream));
+  return 0;
+}
+
+extern "C" int missm_debug_crumb(const char* what_static, void* stream) {
+  if (g_debug_events) crumb(what_static, 0, stream);
+  return 0;
+}
+
+// debugging aid: for every stream, the first recorded call whose event has not completed (see `crumb` above)
+extern "C" int missm_debug_dump(void) {
+  std::lock_guard<std::mutex> lk(g_crumb_mu);
+  std::vector<void*> seen;
+  fprintf(stderr, "missm_debug_dump: %zu recorded calls\n", g_crumbs.size());
+  for (size_t i = 0; i < g_crumbs.size(); ++i) {
+    const Crumb& c = g_crumbs[i];
+    bool done = false;
+    for (void* s : seen) done = done || s == c.stream;
+    if (done) continue;
+    if (cudaEventQuery(c.ev) == cudaSuccess) continue;
+    seen.push_back(c.stream);
+    fprintf(stderr, "  stream %p: first unfinished call #%zu (blocks.cu:%d) %.160s\n", c.stream, i, c.line, c.what);
+    for (size_t j = i; j-- > 0;)
+      if (g_crumbs[j].stream == c.stream) {
+        fprintf(stderr, "      previous call on that stream (finished): blocks.cu:%d %.120s\n", g_crumbs[j].line, g_crumbs[j].what);
+        break;
+      }
+  }
   return 0;
 }

@@ -22,6 +22,7 @@
 #include <mutex>
 #include <vector>
 
+#define MISSM_KERNEL_TAG "gemm_1cta"
 #include "../../include/missm_b200.h"
 #include "gemm_common.cuh"
 #include "missm_common.cuh"
@@ -431,7 +432,8 @@ static int gemm_bf16_impl(const missm_gemm_args* a, void* stream_v) {
   // large-M problems go to the CTA-pair kernel (gemm_tcgen05_2cta.cu); MISSM_GEMM_1CTA=1 keeps
   // everything on the single-CTA kernel (A/B measurements)
   static const bool only_1cta = getenv("MISSM_GEMM_1CTA") != nullptr;
-  if (!only_1cta && a->M >= 1024) return gemm_launch_2cta(a, p, stream);
+  // (N < 128: half of a pair's B tile would lie entirely outside the tensor -- the single-CTA kernel takes those)
+  if (!only_1cta && a->M >= 1024 && a->N >= 128) return gemm_launch_2cta(a, p, stream);
   p.num_m_blk = (a->M + BM - 1) / BM;
   p.num_kblk = (a->K + BK - 1) / BK;
 

@@ -26,6 +26,7 @@
 // Bound: tensor pipe.  Algorithmic work per launch = 2*M*N*K flop.
 #include <cstdlib>
 
+#define MISSM_KERNEL_TAG "gemm_2cta"
 #include "../../include/missm_b200.h"
 #include "gemm_common.cuh"
 #include "missm_common.cuh"

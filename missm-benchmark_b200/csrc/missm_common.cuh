@@ -184,11 +184,18 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
   return done != 0;
 }
 // Bounded wait: a protocol bug must surface as a trap (launch failure), never as a hung GPU.
+#ifndef MISSM_MBAR_SPINS
+#define MISSM_MBAR_SPINS (1u << 23)   // try_wait itself suspends for a while; this is seconds, kernels take < 1 ms
+#endif
+#ifndef MISSM_KERNEL_TAG
+#define MISSM_KERNEL_TAG "?"
+#endif
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   uint32_t spins = 0;
   while (!mbar_try_wait(bar, parity)) {
-    if (++spins > (1u << 23)) {  // try_wait itself suspends for a while; this is seconds, kernels take < 1 ms
-      printf("missm: mbarrier wait timeout (block %d thread %d)\n", blockIdx.x, threadIdx.x);
+    if (++spins > MISSM_MBAR_SPINS) {
+      printf("missm: mbarrier wait timeout in %s (block %d of %d, thread %d, barrier @smem+%u, parity %u)\n",
+             MISSM_KERNEL_TAG, blockIdx.x, gridDim.x, threadIdx.x, smem_u32(bar), parity);
       __trap();
     }
   }

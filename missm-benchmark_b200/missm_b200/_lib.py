@@ -87,8 +87,15 @@ def _declare(L):
 CALLS = [0]      # binding calls made so far (one check() per call): bench.py reports them per step
 
 
+_DEBUG_EVENTS = os.environ.get("MISSM_DEBUG_EVENTS") == "2"     # debugging aid, see missm_debug_dump
+_LABELS = {}
+
+
 def check(rc, what=""):
     CALLS[0] += 1
+    if _DEBUG_EVENTS:
+        lab = _LABELS.setdefault(what, what.encode())
+        lib().missm_debug_crumb(lab, stream_ptr())
     if rc != 0:
         msg = lib().missm_last_error().decode("utf-8", "replace")
         raise RuntimeError(f"missm_b200 {what} failed (rc={rc}): {msg}")

@@ -196,7 +196,8 @@ class AttnMeta:
 # The encoder's own weights are frozen by peft, so their wgrads / bias sums are skipped (needs_input_grad).
 # ------------------------------------------------------------------------------------------
 def _pad8(n):
-    return (n + 7) // 8 * 8
+    """LoRA rank groups are padded to 64 columns = one 128-byte K block of the GEMM tiles (see include/missm_b200.h)."""
+    return (n + 63) // 64 * 64
 
 
 def lora_packs(cache, base, adapters, scaling):
@@ -340,7 +341,7 @@ class VisionEmbedFn(torch.autograd.Function):
         ps, T, gh, gw, eps = geom
         D = patch_w.shape[0]
         K = patch_w.shape[1] * ps * ps
-        Kpad = (K + 7) // 8 * 8
+        Kpad = (K + 63) // 64 * 64          # whole 64-element K blocks: no TMA box of the GEMM leaves the tensor
         P = gh * gw
         wp = bf16_weight(cache, "patch", patch_w, cols_dst=Kpad)
         patches = ops.patchify(pixels, ps, Kpad, T, sample_index=present_idx, n_samples=n_present)

@@ -2,6 +2,7 @@
 with missing-modality mask compaction in front of every tower."""
 import contextlib
 import os
+import time
 
 import torch
 from torch import nn
@@ -14,6 +15,10 @@ from . import config as C
 # src/model/baseline.py:8 -- depth / thermal have no code in the reference; BASELINE.json configs 2
 # and 4 use those towers, so the map is extended without touching codes 0-4.
 MISSING_TYPE_INDEX = {'language': 1, 'video': 2, 'audio': 3, 'image': 4, 'depth': 5, 'thermal': 6}
+
+# seconds the host has spent blocked in the per-step compaction read-back (it waits for the GPU to drain the previous
+# step: bench.py subtracts it from the loop's wall time to report what the host needs to ISSUE a step)
+HOST_WAIT_S = [0.0]
 
 config_dict = {
     'thermal': C.LanguageBindThermalConfig, 'image': C.LanguageBindImageConfig,
@@ -147,7 +152,9 @@ class LanguageBind(nn.Module):
             mi = _require_cuda_index(mi, mdev)
             codes = [MISSING_TYPE_INDEX.get(k, -1) for k in keys]
             idx, slot, counts = ops.compact_mask(mi, codes)
+            t0 = time.perf_counter()
             counts = counts.tolist()          # the one host sync of the step: sizes of the towers' batches
+            HOST_WAIT_S[0] += time.perf_counter() - t0
             B = mi.numel()
             for i, k in enumerate(keys):
                 if counts[i] < B:

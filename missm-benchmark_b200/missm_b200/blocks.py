@@ -47,7 +47,8 @@ class MlpBlockArgs(ctypes.Structure):
 
 
 def pad8(n):
-    return (n + 7) // 8 * 8
+    """LoRA rank groups are padded to 64 columns = one 128-byte K block of the GEMM tiles (see include/missm_b200.h)."""
+    return (n + 63) // 64 * 64
 
 
 class AttnWeights:
