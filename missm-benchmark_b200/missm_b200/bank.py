@@ -138,9 +138,10 @@ class LanguageBind(nn.Module):
         """inputs: {modal: {'pixel_values': ...} | {'input_ids', 'attention_mask'}} -> {modal: [B, P]}.
         `missing_index` (int64 [B], optional) enables compaction: a tower only runs the samples whose
         code differs from its own; rows of missing samples come back as zeros."""
-        ddp_sms = _ddp_backward_sms() if torch.is_grad_enabled() else 0
-        if ddp_sms:
-            ops.set_persistent_sms(0)          # forward: no all-reduce in flight, all SMs
+        policy = _ddp_backward_sms()
+        if policy:
+            ops.set_persistent_sms(0)          # forward (also the no_grad evaluation after an epoch): all SMs
+        ddp_sms = policy if torch.is_grad_enabled() else 0
         keys = list(inputs.keys())
         plan = {}
         # HOST inputs are accepted when the model lives on a CUDA device: every tower uploads its own tensors on
@@ -184,7 +185,9 @@ class LanguageBind(nn.Module):
                 if key in plan:
                     pidx, slot, n, B = plan[key]
                     if n == 0:
-                        params = [p for p in list(enc.parameters()) + list(proj.parameters())]
+                        # only parameters that take a gradient (a peft-frozen ViT-L base would otherwise cost
+                        # 1.2 GB of zero-filled gradients that autograd throws away)
+                        params = [p for p in list(enc.parameters()) + list(proj.parameters()) if p.requires_grad]
                         outputs[key] = _ZeroTower.apply(B, proj.weight.shape[0], proj.weight.device, *params)
                     else:
                         y = enc(**value, present_idx=pidx, n_present=n, proj=proj, scale=scale)[1]

@@ -50,6 +50,16 @@ class LoraLinear(nn.Linear):
         nn.init.kaiming_uniform_(self.lora_A['default'].weight, a=math.sqrt(5))
         nn.init.zeros_(self.lora_B['default'].weight)
 
+    def _load_from_state_dict(self, state_dict, prefix, *args):
+        # peft >= 0.6 keeps the frozen Linear under `.base_layer.`; this tree uses the 0.4 / 0.5 layout (the wrapper IS
+        # the Linear).  The reference does not pin peft, so a `final_model/*.pth` written by either loads through the
+        # plain nn.Module.load_state_dict the scripts call (test.py:92, train_ddp.py:193).
+        for name in ('weight', 'bias'):
+            k = prefix + 'base_layer.' + name
+            if k in state_dict:
+                state_dict[prefix + name] = state_dict.pop(k)
+        super()._load_from_state_dict(state_dict, prefix, *args)
+
     @property
     def A(self):
         return self.lora_A['default'].weight
@@ -87,6 +97,14 @@ class PeftModel(_Wrapped):
     def __init__(self, model):
         super().__init__()
         self.base_model = LoraModel(model)
+
+    def _load_from_state_dict(self, state_dict, prefix, *args):
+        # a checkpoint of the UNWRAPPED encoder (`...encoder.layers.N...`: lora_r = 0, or adapters merged before
+        # saving) loads into the wrapped tree: its keys move under `base_model.model.`
+        inner = prefix + 'base_model.model.'
+        for k in [k for k in state_dict if k.startswith(prefix) and not k.startswith(prefix + 'base_model.')]:
+            state_dict[inner + k[len(prefix):]] = state_dict.pop(k)
+        super()._load_from_state_dict(state_dict, prefix, *args)
 
 
 class CLIPAttention(nn.Module):

@@ -198,3 +198,30 @@ def test_checkpoint_key_layouts():
     for n, p in lora.named_parameters():
         inside = n.startswith('vision_model.encoder.')
         assert p.requires_grad == (not inside or '.lora_' in n), n
+
+
+def test_finetune_checkpoint_round_trips_both_peft_layouts(gold):
+    """`final_model/<ds>_<fusion>.pth` files go through a plain, STRICT finetune_model.load_state_dict in the scripts
+    (test.py:92, train_ddp.py:193,317).  The reference does not pin peft: a checkpoint written under peft >= 0.6
+    spells the frozen Linear `...q_proj.base_layer.weight`, one written under 0.4 / 0.5 `...q_proj.weight`.  Both
+    must load strictly, and a checkpoint of the unwrapped encoder must load non-strictly (adapters stay no-ops)."""
+    model, sd, _, _, _ = make_model(gold['meta'])
+    own = {k: v.clone() for k, v in model.state_dict().items()}
+    new_layout = {}
+    for k, v in own.items():
+        head, leaf = k.rsplit('.', 1)
+        if 'base_model.model' in k and head.rsplit('.', 1)[-1] in ('q_proj', 'k_proj', 'v_proj', 'out_proj') and \
+                leaf in ('weight', 'bias') and (head + '.lora_A.default.weight') in own:
+            k = head + '.base_layer.' + leaf
+        new_layout[k] = v.clone() + 0.5
+    assert any('.base_layer.' in k for k in new_layout)
+    res = model.load_state_dict(new_layout)                      # strict, as the scripts call it
+    assert not res.missing_keys and not res.unexpected_keys
+    for k, v in model.state_dict().items():
+        assert torch.equal(v, own[k] + 0.5) or not v.is_floating_point(), k
+    res = model.load_state_dict({k: v - 0.5 for k, v in model.state_dict().items()})     # 0.4 / 0.5 layout: strict too
+    assert not res.missing_keys and not res.unexpected_keys
+    # unwrapped-encoder keys (`...encoder.layers.N...`): accepted, only the adapters are reported missing
+    plain = {k.replace('.encoder.base_model.model.', '.encoder.'): v for k, v in model.state_dict().items() if '.lora_' not in k}
+    res = model.load_state_dict(plain, strict=False)
+    assert not res.unexpected_keys and res.missing_keys and all('.lora_' in k for k in res.missing_keys)
