@@ -38,7 +38,8 @@ def parse():
     ap.add_argument("--impl", default="missm", choices=["missm", "reference"])
     ap.add_argument("--batch", type=int, default=64, help="samples per GPU")
     ap.add_argument("--missing", type=float, default=0.3)
-    ap.add_argument("--cpu-baseline-samples", type=int, default=2)
+    ap.add_argument("--cpu-baseline-samples", type=int, default=0,
+                    help="samples per CPU step (0 = auto: 2 for the cpu_baseline leg, 2..8 for --impl reference)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--layers", type=int, default=24, help=argparse.SUPPRESS)  # debugging only
@@ -74,8 +75,42 @@ def peaks():
 # ------------------------------------------------------------------------------------------------
 # CPU arm: the oracle port (oracle/restatement.py) of the reference path on the host cores
 # ------------------------------------------------------------------------------------------------
+def reference_step_fn(n_samples, layers=24):
+    """One fwd+bwd of the workload on `n_samples` samples through the UNMODIFIED reference: its own LanguageBind
+    bank (languagebind/__init__.py:54-85), finetune_model + `sum` head (src/model/baseline.py:43-61, 421-453) and
+    CLIP towers, imported from /root/reference (build container) or its staged copy oracle/_ref (GPU box) through
+    oracle/ref_shim.py, fp32 on the host cores, full batch through every tower (the reference never skips missing
+    samples).  Returns None when neither tree is present."""
+    import torch
+    import ref_shim
+    import restatement as R
+    from missm_b200 import config as C
+    if not ref_shim.available():
+        return None
+    v = dict(C.VIT_L14, lora_r=0, num_hidden_layers=layers)
+    bank = ref_shim.build_reference_bank(MODALS, v, dict(C.CLIP_TEXT), projection_dim=768)
+    model = ref_shim.build_reference_model(bank, 'sum', MODALS, 3, feature_dims=768, fusion_dim=256, dropout_prob=0.1,
+                                           extra_missing_codes={'depth': 5, 'thermal': 6})
+    sd = R.synth_state_dict([(k, tuple(t.shape)) for k, t in model.state_dict().items()])
+    model.load_state_dict(sd, strict=False)
+    del sd
+    model.train()
+    cfgs, tcfg = full_configs(layers)
+    data = R.synth_inputs(MODALS, n_samples, cfgs, tcfg, seed=0)
+    mi = R.synth_missing_index(n_samples, 0.3, MODALS)
+    labels = torch.arange(n_samples) % 3
+    crit = torch.nn.CrossEntropyLoss()
+
+    def step():
+        model.zero_grad(set_to_none=True)
+        loss = crit(model({k: dict(d) for k, d in data.items()}, mi), labels)
+        loss.backward()
+        return float(loss.detach())
+    return step
+
+
 def cpu_step_fn(n_samples, layers=24):
-    """Returns (step_fn, description): one fwd+bwd of the same workload on `n_samples` samples."""
+    """The oracle PORT of the same step (oracle/restatement.py) -- the fallback when the reference tree is absent."""
     import torch
     import restatement as R
     from missm_b200 import shapes
@@ -94,14 +129,23 @@ def cpu_step_fn(n_samples, layers=24):
         for v in sd.values():
             v.grad = None
         loss.backward()
-        return float(loss)
+        return float(loss.detach())
     return step
 
 
+def cpu_arm(n_samples, layers):
+    """-> (step_fn, kind, what): the reference itself when its tree is present, else the oracle port."""
+    step = reference_step_fn(n_samples, layers)
+    if step is not None:
+        import ref_shim
+        return step, "reference", f"unmodified reference ({ref_shim.REFERENCE_ROOT}: languagebind + src.model through oracle/ref_shim.py)"
+    return cpu_step_fn(n_samples, layers), "port", "oracle/restatement.py"
+
+
 def run_reference_arm(a):
-    """The reference's own CPU implementation of the path (the oracle port of it: the reference is
-    Python that needs /root/reference + an import shim and cannot travel to the GPU box), all host
-    threads, fp32, full batch through every tower (the reference never skips missing samples)."""
+    """The reference's own CPU implementation of the path, all host threads, fp32, full batch through every tower
+    (the reference never skips missing samples).  A step is a bounded sample of the B = 64 workload: as many samples
+    (2..8) as keep the whole --steps K --warmup W run within a few minutes."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
@@ -109,7 +153,9 @@ def run_reference_arm(a):
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
     n = a.cpu_baseline_samples
-    step = cpu_step_fn(n, a.layers)
+    if n <= 0:      # auto: ~1.1 samples/s on the 16 host cores of the GPU box -> about 200 s for the whole run
+        n = max(2, min(8, int(220 / max(1, a.steps + a.warmup))))
+    step, kind, what = cpu_arm(n, a.layers)
     for _ in range(a.warmup):
         step()
     t0 = time.perf_counter()
@@ -121,9 +167,10 @@ def run_reference_arm(a):
         "impl": "reference", "metric": METRIC, "value": val, "unit": "samples/s", "n_gpus": a.gpus,
         "steps": a.steps, "warmup": a.warmup, "ms_per_step": dt / a.steps * 1e3, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "sample": f"{n} samples per step (bounded CPU sample of the B=64 workload)"},
-        "cpu_baseline": {"value": val, "unit": "samples/s", "cores": cores, "kind": "port",
-                         "sample": f"{n} samples x 3 full-size towers fwd+bwd per step, {a.steps} steps"},
+        "config": {"workload": WORKLOAD, "sample": f"{n} samples per step (bounded CPU sample of the B=64 workload)",
+                   "implementation": what},
+        "cpu_baseline": {"value": val, "unit": "samples/s", "cores": cores, "kind": kind,
+                         "sample": f"{n} samples x 3 full-size towers fwd+bwd per step, {a.steps} steps; {what}"},
         "e2e": {"value": val, "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -328,14 +375,14 @@ def run_gpu_arm(a):
         torch.cuda.empty_cache()
         cores = os.cpu_count() or 1
         torch.set_num_threads(cores)
-        n = a.cpu_baseline_samples
-        stepc = cpu_step_fn(n, a.layers)
+        n = a.cpu_baseline_samples if a.cpu_baseline_samples > 0 else 2
+        stepc, kind, what = cpu_arm(n, a.layers)
         stepc()
         t0 = time.perf_counter()
         stepc()
         dt = time.perf_counter() - t0
-        cpu_base = {"value": n / dt, "unit": "samples/s", "cores": cores, "kind": "port",
-                    "sample": f"{n} samples x 3 full-size towers fwd+bwd, fp32, oracle/restatement.py, 1 warm-up + 1 timed"}
+        cpu_base = {"value": n / dt, "unit": "samples/s", "cores": cores, "kind": kind,
+                    "sample": f"{n} samples x 3 full-size towers fwd+bwd, fp32, {what}, 1 warm-up + 1 timed"}
 
     if rank == 0:
         # fwd+bwd = 3 x forward flops; with a frozen (LoRA) encoder the weight gradients are not computed: 2 x

@@ -1,8 +1,9 @@
-"""TEST INFRASTRUCTURE ONLY -- import shim for the *unmodified* reference Python files.
+"""TEST / MEASUREMENT INFRASTRUCTURE ONLY -- import shim for the *unmodified* reference Python files.
 
-Used only inside this build container (where /root/reference exists) by
-oracle/make_golden.py to generate golden vectors and to pin oracle/restatement.py.
-It never travels to the GPU box and nothing in the product path imports it.
+Used (a) inside the build container (where /root/reference exists) by oracle/make_golden.py to generate golden
+vectors and to pin oracle/restatement.py, and (b) by bench.py's CPU legs (`--impl reference`, `cpu_baseline`), which
+time the reference's own code on the host cores: on the GPU box the reference is the byte-identical copy that
+oracle/stage_reference.py staged into the git-ignored oracle/_ref/.  Nothing in the product path imports it.
 
 Why a shim is needed: the reference binds third-party
 names at import time (languagebind/image/modeling_image.py:5-15) that do not exist in this
@@ -12,13 +13,22 @@ convention with `causal_attention_mask=`, and a `CLIPVisionEmbeddings` without t
 square-input check).  The third-party arithmetic is re-stated here from its published
 algorithm (transformers 4.31-4.34 `modeling_clip.py`; version unpinned by the reference).
 """
+import os
 import sys
 import types
 
 import torch
 from torch import nn
 
-REFERENCE_ROOT = "/root/reference"
+_HERE = os.path.dirname(os.path.abspath(__file__))
+# the reference tree itself in the build container, else the copy staged by oracle/stage_reference.py
+REFERENCE_ROOT = os.environ.get("MISSM_REFERENCE_ROOT") or (
+    "/root/reference" if os.path.isdir("/root/reference/languagebind") else os.path.join(_HERE, "_ref"))
+
+
+def available():
+    return os.path.isdir(os.path.join(REFERENCE_ROOT, "languagebind")) and \
+        os.path.isfile(os.path.join(REFERENCE_ROOT, "src", "model", "baseline.py"))
 
 
 def _stub(name, **attrs):

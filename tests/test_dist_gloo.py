@@ -163,4 +163,7 @@ def test_reference_arm_under_torchrun_prints_one_line():
     assert len(lines) == 1, r.stdout
     d = json.loads(lines[0])
     assert d["impl"] == "reference" and d["unit"] == "samples/s" and d["value"] > 0
-    assert d["cpu_baseline"]["kind"] == "port" and d["e2e"]["h2d_bytes_per_step"] == 0
+    # the reference tree (or its staged copy oracle/_ref) is present wherever build() ran: the arm times the reference itself
+    assert d["cpu_baseline"]["kind"] in ("reference", "port") and d["e2e"]["h2d_bytes_per_step"] == 0
+    if os.path.isdir("/root/reference/languagebind") or os.path.isdir(os.path.join(ROOT, "oracle", "_ref", "languagebind")):
+        assert d["cpu_baseline"]["kind"] == "reference"

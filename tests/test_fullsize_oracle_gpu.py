@@ -21,6 +21,19 @@ import restatement as R  # noqa: E402  (the checker, never the thing measured)
 from test_parity_gpu import DEV, TOL, TOL_GRAD, TOL_LOGIT, make, rel, to_dev  # noqa: E402
 
 
+# bf16 mode, gradients of the 24-layer towers.  With name-seeded random weights the 24-layer towers map every input
+# to nearly the same embedding (cosine 0.96 between samples), so the loss gradient lives in small differences and is
+# ILL-CONDITIONED with respect to the forward tolerance: perturbing the oracle's OWN embeddings by 5e-3 (half of
+# north_star's 1e-2; the bf16 path measures 5e-3) moves the oracle's own head / d_embedding gradients by 7-12 %
+# (scratch/grad_conditioning.py, ReLU / LayerNorm nonlinearity of the head).  So the test bounds three things:
+#   (a) fp32 verification mode vs the oracle <= 1e-4 on every tensor        -> the backward formulas are right;
+#   (b) bf16 head gradients vs the oracle head evaluated AT THE PRODUCT'S embeddings <= 2e-3 -> nothing but the
+#       forward difference explains the head's deviation;
+#   (c) bf16 tower gradients vs the oracle: relative error <= 0.25 and cosine >= 0.96 (measured 0.09-0.21).
+TOL_GRAD_DEEP = 0.25
+COS_GRAD_DEEP = 0.96
+
+
 def _oracle_step(sd, modal, data, mi, cfgs, tcfg, labels):
     sdg = {k: t.clone().requires_grad_(t.is_floating_point()) for k, t in sd.items()}
     logits, emb = R.finetune_forward(sdg, 'sum', modal, data, mi, cfgs, tcfg, {m: 2.6592 for m in cfgs})
@@ -44,17 +57,26 @@ def _product_step(model, data, mi, labels):
     return logits.detach(), emb, loss.detach()
 
 
-def _check_grads(model, sdg, names, tol):
+def _check_grads(model, sdg, names, tol, tag='', cos_min=None, loose=None):
+    """`loose`: {substring: tolerance} for tensors with a known cancellation (stated at the call site)."""
     params = dict(model.named_parameters())
-    worst = (0.0, None)
+    errs, bad = [], []
     for n in names:
         ref = sdg[n].grad
         assert ref is not None and ref.norm() > 0, n
-        e = rel(params[n].grad, ref)
-        print(f'   grad {n}: rel {e:.2e}')
-        worst = max(worst, (e, n))
-        assert e < tol, (n, e)
-    return worst
+        g = params[n].grad.detach().float().cpu()
+        e = rel(g, ref)
+        c = torch.nn.functional.cosine_similarity(g.flatten(), ref.flatten(), dim=0).item()
+        print(f'   {tag}grad {n}: rel {e:.2e} cos {c:.4f}')
+        errs.append((e, n))
+        t = tol
+        for sub, lt in (loose or {}).items():
+            if sub in n:
+                t = lt
+        if not e < t or (cos_min is not None and not c > cos_min):
+            bad.append((e, c, n))
+    assert not bad, bad
+    return max(errs)
 
 
 def test_config2_full_depth_fwd_bwd_vs_oracle():
@@ -88,7 +110,34 @@ def test_config2_full_depth_fwd_bwd_vs_oracle():
                   p + 'embeddings.position_embedding.weight', p + 'embeddings.class_embedding',
                   p + 'encoder.layers.11.mlp.fc1.weight', p + 'encoder.layers.23.self_attn.out_proj.bias']
     names += ['fusion.modal_proj.image.weight', 'fusion.head.head.0.weight', 'encoder.modality_proj.depth.weight']
-    worst = _check_grads(model, sdg, names, TOL_GRAD)
+    # (a) fp32 verification mode first: the same 24-layer step with fp32-grade arithmetic must reproduce the oracle's
+    #     gradients to 1e-4 -- every backward formula / operand layout of the path is right at full size
+    from missm_b200 import autograd as ag
+    old = ag.set_precision("fp32")
+    try:
+        model.zero_grad(set_to_none=True)
+        logits32, emb32, loss32 = _product_step(model, data, mi, labels)
+        for m in modal:
+            present = mi != code[m]
+            assert rel(emb32[m][present.to(DEV)], ref_emb[m][present]) < 1e-5, m
+        assert abs(loss32.item() - ref_loss.item()) < 1e-5 * abs(ref_loss.item())
+        worst32 = _check_grads(model, sdg, names, 1e-4, 'fp32 mode ')
+    finally:
+        ag.set_precision(old)
+    print('config2 full depth, fp32 mode: worst gradient', worst32)
+    # (b) the product's bf16 mode: head gradients against the oracle head evaluated at the product's OWN embeddings
+    model.zero_grad(set_to_none=True)
+    _, emb_p, _ = _product_step(model, data, mi, labels)
+    hs = {k: t.detach().clone().requires_grad_(True) for k, t in sd.items() if k.startswith('fusion.')}
+    lg = R.fusion_forward(hs, 'sum', modal, {m: emb_p[m].float().cpu() for m in modal}, mi)
+    torch.nn.functional.cross_entropy(lg, labels).backward()
+    params = dict(model.named_parameters())
+    for k, t in hs.items():
+        e = rel(params[k].grad, t.grad)
+        print(f'   head grad at the product embeddings {k}: rel {e:.2e}')
+        assert e < 2e-3, (k, e)
+    # (c) every tensor against the full oracle
+    worst = _check_grads(model, sdg, names, TOL_GRAD_DEEP, cos_min=COS_GRAD_DEEP)
     print('config2 full depth: worst gradient', worst)
 
 
@@ -119,5 +168,19 @@ def test_config3_audio_video_gradients_vs_oracle():
              v + 'encoder.layers.0.self_attn.v_proj.bias', v + 'embeddings.patch_embedding.weight',
              v + 'embeddings.position_embedding.weight', 'encoder.modality_proj.video.weight',
              'fusion.modal_proj.audio.weight']
-    worst = _check_grads(model, sdg, names, TOL_GRAD)
+    from missm_b200 import autograd as ag
+    old = ag.set_precision("fp32")
+    try:
+        model.zero_grad(set_to_none=True)
+        _product_step(model, data, mi, labels)
+        worst32 = _check_grads(model, sdg, names, 1e-4, 'fp32 mode ')
+    finally:
+        ag.set_precision(old)
+    print('config3, fp32 mode: worst gradient', worst32)
+    model.zero_grad(set_to_none=True)
+    _product_step(model, data, mi, labels)
+    # temporal attention runs over T = 8 frames of nearly identical synthetic tokens: its softmax is nearly uniform and
+    # dS = P o (dP - delta) is a difference of nearly equal numbers -- the q / k projection gradients of that block carry
+    # the bf16 rounding of P amplified (measured 0.16; 1e-4 in the fp32 mode above); everything else <= 3e-2
+    worst = _check_grads(model, sdg, names, TOL_GRAD, loose={'temporal_attn.q_proj': 0.25, 'temporal_attn.k_proj': 0.25})
     print('config3: worst gradient', worst)
