@@ -441,14 +441,18 @@ def run_gpu_arm(a):
         cores = os.cpu_count() or 1
         torch.set_num_threads(cores)
         n = a.cpu_baseline_samples if a.cpu_baseline_samples > 0 else 2
-        stepc, kind, what = cpu_arm(n, a.layers, MODALS, train)
-        stepc()
-        t0 = time.perf_counter()
-        stepc()
-        dt = time.perf_counter() - t0
-        cpu_base = {"value": n * (len(SWEEP) if not train else 1) / dt, "unit": "samples/s", "cores": cores, "kind": kind,
-                    "sample": f"{n} samples x {len(MODALS)} full-size towers {'fwd+bwd' if train else 'eval sweep'}, fp32, {what}, "
-                              f"1 warm-up + 1 timed"}
+        # in its own process: the reference's `languagebind` / `src` packages share their names with the drop-in
+        # packages this process has imported
+        r = subprocess.run([sys.executable, os.path.abspath(__file__), "--impl", "reference", "--config", str(a.config),
+                            "--layers", str(a.layers), "--steps", "1", "--warmup", "1", "--cpu-baseline-samples", str(n)],
+                           capture_output=True, text=True, timeout=900)
+        lines = [ln for ln in r.stdout.splitlines() if ln.startswith("{")]
+        if r.returncode == 0 and lines:
+            cpu_base = json.loads(lines[-1])["cpu_baseline"]
+            cpu_base["sample"] = cpu_base["sample"].replace("1 steps", "1 warm-up + 1 timed step")
+        else:
+            cpu_base = {"value": None, "unit": "samples/s", "cores": cores, "kind": "unavailable",
+                        "sample": "the CPU leg failed: " + r.stderr[-300:]}
 
     if rank == 0:
         # fwd+bwd = 3 x forward flops; with a frozen (LoRA) encoder the weight gradients are not computed: 2 x

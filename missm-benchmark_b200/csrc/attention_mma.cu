@@ -519,10 +519,17 @@ using namespace missm;
 namespace missm {
 int attention_fwd_tc(const missm_attn_args* a, cudaStream_t stream);  // attention_tc.cu
 int attention_bwd_tc(const missm_attn_args* a, cudaStream_t stream);  // attention_tc_bwd.cu
+int attention_fwd_small(const missm_attn_args* a, cudaStream_t stream);   // attention_small.cu (N <= 8)
+int attention_bwd_small(const missm_attn_args* a, cudaStream_t stream);
 }
 
 extern "C" int missm_attention_fwd(const missm_attn_args* a, void* stream) {
   if (a->n_seq == 0) return 0;
+  MISSM_REQUIRE(a->qkv && a->out, "attention_fwd: null tensor");
+  {   // short sequences (temporal attention of the video tower): one warp per (sequence, head)
+    const int rc = attention_fwd_small(a, static_cast<cudaStream_t>(stream));
+    if (rc >= 0) return rc;
+  }
   // tcgen05 path for the shapes it covers (spatial ViT attention); general shapes below
   static const bool legacy_only = getenv("MISSM_ATTN_LEGACY") != nullptr || getenv("MISSM_ATTN_LEGACY_FWD") != nullptr;
   if (!legacy_only) {
@@ -549,6 +556,10 @@ extern "C" int missm_attention_bwd(missm_attn_args* a, void* stream) {
   const long total = static_cast<long>(p.n_seq) * p.H * p.N;
   int dgrid = static_cast<int>((total + 255) / 256);
   if (dgrid > 16 * kNumSMs) dgrid = 16 * kNumSMs;
+  {
+    const int rc = attention_bwd_small(a, st);    // short sequences: one warp per (sequence, head), no delta pass
+    if (rc >= 0) return rc;
+  }
   static const bool legacy_only = getenv("MISSM_ATTN_LEGACY") != nullptr || getenv("MISSM_ATTN_LEGACY_BWD") != nullptr;
   if (!legacy_only) {
     const int rc = attention_bwd_tc(a, st);   // tcgen05 path for the shapes it covers (computes delta itself)

@@ -19,9 +19,13 @@ ap.add_argument("--modals", default="image,depth,thermal")
 ap.add_argument("--batch", type=int, default=64)
 a = ap.parse_args()
 MODALS = a.modals.split(",")
-v = {k: val for k, val in C.VIT_L14.items() if k != 'lora_r'}
-v['num_hidden_layers'] = a.layers
-cfgs = {m: R.vision_config(**v) for m in MODALS}
+cfgs = {}
+for m in MODALS:
+    v = {k: val for k, val in C.VIT_L14.items() if k != 'lora_r'}
+    v['num_hidden_layers'] = a.layers
+    v.update(C.SYNTHETIC_PER_MODALITY[m])
+    v['temporal_mlp'] = (m != 'video')
+    cfgs[m] = R.vision_config(**v)
 tcfg = R.text_config(**dict(C.CLIP_TEXT, num_hidden_layers=1))
 model = shapes.build_finetune(cfgs, tcfg, MODALS, 'sum', 3, 768, 256, dropout_prob=0.1)
 sd = R.synth_state_dict([(k, tuple(t.shape)) for k, t in model.state_dict().items()])

@@ -198,18 +198,31 @@ def test_attention_fwd_bwd(ops, cfg):
     assert rel(dcs, gref.sum(0)) < 1.5e-2               # q/k/v bias gradients
 
 
-def test_attention_temporal_layout(ops):
-    """Temporal attention reads [(b t) n d] in place: sequence (b, n) over t."""
-    torch.manual_seed(5)
-    B, T, N, H = 2, 8, 5, 2
+@pytest.mark.parametrize("T", [8, 5, 3, 1])
+def test_attention_temporal_layout(ops, T):
+    """Temporal attention reads [(b t) n d] in place: sequence (b, n) over t.  T <= 8 runs the one-warp-per-
+    (sequence, head) kernel of csrc/attention_small.cu, forward and backward, vs fp32 torch autograd."""
+    torch.manual_seed(5 + T)
+    B, N, H = 2, 5, 2
     D = H * 64
     qkv = (torch.randn(B * T * N, 3 * D, device=DEV) * 0.7).bfloat16()
     lay = ops.SeqLayout.temporal(B, T, N)
     out, lse = ops.attention_fwd(qkv, lay, H)
-    f = qkv.float().view(B, T, N, 3, H, 64).permute(3, 0, 2, 4, 1, 5).reshape(3, B * N, H, T, 64)
+    f = qkv.float().view(B, T, N, 3, H, 64).permute(3, 0, 2, 4, 1, 5).reshape(3, B * N, H, T, 64).contiguous()
+    f.requires_grad_(True)
     ref = _attn_ref(f[0], f[1], f[2], False, None)           # [(b n), H, T, hd]
     ref_o = ref.view(B, N, H, T, 64).permute(0, 3, 1, 2, 4).reshape(B * T * N, D)
     assert rel(out, ref_o) < 6e-3
+    lse_ref = torch.logsumexp(f[0].detach() @ f[1].detach().transpose(-1, -2), -1)      # [(b n), H, T]
+    assert (lse - lse_ref).abs().max() < 2e-2
+    d_out = torch.randn(B * T * N, D, device=DEV).bfloat16()
+    ref_o.backward(d_out.float())
+    dqkv, dcs = ops.attention_bwd(qkv, out, lse, d_out, lay, H, 0.125)
+    g = f.grad.view(3, B, N, H, T, 64).permute(1, 4, 2, 0, 3, 5).reshape(B * T * N, 3 * D).clone()
+    g[:, :D] *= 0.125
+    for c in range(3):
+        assert rel(dqkv[:, c * D:(c + 1) * D], g[:, c * D:(c + 1) * D]) < 1.5e-2, c
+    assert rel(dcs, g.sum(0)) < 1.5e-2
 
 
 # --------------------------------------------------------------------------------- helpers
