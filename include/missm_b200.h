@@ -393,6 +393,17 @@ int missm_mlp_block_fwd(const missm_mlp_block_args* args, void* stream);
 int missm_mlp_block_bwd(const missm_mlp_block_args* args, void* stream);
 
 /* ---------------------------------------------------------------------------------------
+ * Evaluation metrics accumulated on the device (csrc/metrics.cu) -- replaces the per-batch host round trips of the
+ * reference's evaluate() (train_ddp.py:88-133, test.py:21-66: `loss.item()`, argmax / softmax `.cpu().numpy()` every
+ * batch).  One launch per batch: confusion[label, argmax] += 1 (int64 [C, C], first maximum as torch.argmax),
+ * loss_sum += mean CrossEntropy of the batch (double), probs[b, :] = softmax(logits[b, :]) (for roc_auc_score),
+ * n_seen += B.  Accuracy and macro-F1 follow from the confusion matrix at the epoch's single read-out
+ * (missm_b200/metrics.py).  logits f32 [B, C] contiguous, labels int64 [B]; accumulators are caller-zeroed.
+ * ------------------------------------------------------------------------------------- */
+int missm_eval_accumulate(const float* logits, const int64_t* labels, int32_t B, int32_t C, float* probs,
+                          int64_t* confusion, double* loss_sum, int64_t* n_seen, void* stream);
+
+/* ---------------------------------------------------------------------------------------
  * Measurement hooks (bench.py): the number of kernels this library has launched since the last reset, and CUDA
  * events around every missm_gemm_bf16 launch (on the launching stream) while the profile is on.
  * missm_gemm_profile(1) starts (and clears), missm_gemm_profile(0) stops; missm_gemm_profile_read synchronises the
