@@ -393,6 +393,42 @@ int missm_mlp_block_fwd(const missm_mlp_block_args* args, void* stream);
 int missm_mlp_block_bwd(const missm_mlp_block_args* args, void* stream);
 
 /* ---------------------------------------------------------------------------------------
+ * GPU input pipeline, video and audio (csrc/preprocess_av.cu).
+ * missm_video_preprocess: the transform chain of languagebind/video/processing_video.py:25-66 on the decoded frames of
+ *   one clip: x / 255 -> Normalize(mean, std) -> ShortSideScale(S) (bilinear, align_corners = False, no antialias)
+ *   -> CenterCrop(S) -> optional horizontal flip.  src: device uint8 [T, H, W, 3]; dst: device f32 [3, T, S, S].
+ * missm_audio_fbank: torchaudio.compliance.kaldi.fbank as audio/processing_audio.py:96-110 calls it (16 kHz: 400-sample
+ *   hanning frames every 160 samples, DC removal, pre-emphasis 0.97, 512-point power spectrum, n_mel triangular mel
+ *   filters given by the caller as mel_weights f32 [n_mel, 257], log) followed by waveform2melspec's tail (:53-94):
+ *   out[c, m, t] = (mel[(offsets[c] + t) % n_frames, m] - mean) / (2 std), f32 [3, n_mel, target].  wave: channel 0
+ *   (n_samples); wave_all / n_total: the whole loaded tensor whose mean is subtracted first (`audio_data -=
+ *   audio_data.mean()`); mel: workspace f32 [missm_fbank_num_frames(n_samples), n_mel]; wave_sum: workspace, 1 double.
+ * ------------------------------------------------------------------------------------- */
+typedef struct missm_video_args {
+  const void* src;
+  float* dst;
+  int32_t T, H, W, S, hflip;
+  float mean[3];
+  float std_[3];
+} missm_video_args;
+int missm_video_preprocess(const missm_video_args* args, void* stream);
+
+typedef struct missm_fbank_args {
+  const float* wave;
+  const float* wave_all;
+  int64_t n_samples, n_total;
+  const float* mel_weights;
+  float* mel;
+  double* wave_sum;
+  float* out;
+  int32_t n_mel, target;
+  int32_t offsets[3];
+  float mean, std_;
+} missm_fbank_args;
+int missm_fbank_num_frames(int64_t n_samples);
+int missm_audio_fbank(const missm_fbank_args* args, void* stream);
+
+/* ---------------------------------------------------------------------------------------
  * Evaluation metrics accumulated on the device (csrc/metrics.cu) -- replaces the per-batch host round trips of the
  * reference's evaluate() (train_ddp.py:88-133, test.py:21-66: `loss.item()`, argmax / softmax `.cpu().numpy()` every
  * batch).  One launch per batch: confusion[label, argmax] += 1 (int64 [C, C], first maximum as torch.argmax),

@@ -53,6 +53,9 @@ SIGNATURES = {
     "missm_mlp_block_sizes": [P, P],
     "missm_mlp_block_fwd": [P, P],
     "missm_mlp_block_bwd": [P, P],
+    "missm_video_preprocess": [P, P],
+    "missm_fbank_num_frames": [L],
+    "missm_audio_fbank": [P, P],
     "missm_eval_accumulate": [P, P, I, I, P, P, P, P, P],
     "missm_debug_dump": [],
     "missm_debug_crumb": [ctypes.c_char_p, P],

@@ -14,9 +14,15 @@ reference's era) to True (>= 0.17, what the reference computes when run in this 
 the reference as run in this image (True); MISSM_RESIZE_ANTIALIAS=0 selects the older behaviour.  Both are pinned
 against torchvision in the tests.
 
-Video (decord + pytorchvideo) and audio (torchaudio kaldi fbank) processors are not built: they keep the import
-surface and raise with a pointer to the reference's own file.
+Video and audio (second half of the same row): decoding stays on the host with the reference's own decoders (OpenCV /
+decord frame grab at np.linspace(0, n - 1, num_frames) indices, video/processing_video.py:84-109; torchaudio.load,
+audio/processing_audio.py:21-22), everything after the decode runs on the device: the clip's frames go up as uint8
+and ONE launch of `missm_video_preprocess` does x / 255 -> Normalize -> ShortSideScale(224) -> CenterCrop(224) -> flip;
+the waveform goes up once and `missm_audio_fbank` does kaldi fbank + chunk / repeat + normalise (csrc/preprocess_av.cu).
+pytorchvideo's ShortSideScale (absent here, unpinned) is restated from its published algorithm; torchaudio's kaldi
+fbank is pinned against torchaudio itself in the tests.
 """
+import math
 import os
 
 import torch
@@ -149,12 +155,153 @@ class LanguageBindDepthProcessor(_ImageLikeProcessor):
         return dict(pre_div=1000.0, clip_lo=0.01, clip_hi=max_depth, post_div=max_depth)
 
 
-class LanguageBindVideoProcessor(_Processor):
+class _ClipProcessor(_Processor):
+    """Shared __call__ of the reference's video / audio processors (processing_video.py:124-147,
+    processing_audio.py:137-160): a list of paths -> stacked `pixel_values`."""
+
+    def one(self, item):
+        raise NotImplementedError
+
+    def __call__(self, images=None, text=None, context_length=77, return_tensors=None, **kwargs):
+        if text is None and images is None:
+            raise ValueError("You have to specify either text or images. Both cannot be none.")
+        encoding = None
+        if text is not None:
+            encoding = self.tokenizer(text, max_length=context_length, padding='max_length', truncation=True,
+                                      return_tensors=return_tensors, **kwargs)
+        feats = None
+        if images is not None:
+            feats = torch.stack([self.one(x) for x in make_list_of_images(images)])
+        if text is not None and images is not None:
+            encoding["pixel_values"] = feats
+            return encoding
+        return encoding if text is not None else {"pixel_values": feats}
+
+    def batch_decode(self, skip_special_tokens=True, *args, **kwargs):
+        return self.tokenizer.batch_decode(*args, skip_special_tokens=skip_special_tokens, **kwargs)
+
+    def decode(self, skip_special_tokens=True, *args, **kwargs):
+        return self.tokenizer.decode(*args, skip_special_tokens=skip_special_tokens, **kwargs)
+
+
+def _need_cuda(who):
+    if not torch.cuda.is_available():
+        raise RuntimeError(f"missm_b200: {who} preprocesses on the GPU and found no CUDA device (there is no CPU fallback)")
+
+
+class LanguageBindVideoProcessor(_ClipProcessor):
     modality = "video"
+    size = 224
+
+    def decode_frames(self, path):
+        """-> uint8 [T, H, W, 3] RGB frames at np.linspace(0, n - 1, num_frames) (processing_video.py:84-109)."""
+        import numpy as np
+        vc = self.config.vision_config
+        if torch.is_tensor(path) or isinstance(path, np.ndarray):       # already decoded frames
+            t = path if torch.is_tensor(path) else torch.from_numpy(path)
+            if t.dim() != 4 or t.shape[3] != 3 or t.dtype != torch.uint8:
+                raise ValueError(f"decoded frames must be uint8 [T, H, W, 3], got {t.dtype} {tuple(t.shape)}")
+            return t
+        backend = vc.video_decode_backend
+        if backend == 'opencv':
+            import cv2
+            vr = cv2.VideoCapture(path)
+            n = int(vr.get(cv2.CAP_PROP_FRAME_COUNT))
+            frames = []
+            for i in np.linspace(0, n - 1, vc.num_frames, dtype=int):
+                vr.set(1, int(i))
+                ok, frame = vr.read()
+                if not ok:
+                    raise IOError(f"cannot read frame {i} of {path}")
+                frames.append(torch.from_numpy(cv2.cvtColor(frame, cv2.COLOR_BGR2RGB)))
+            vr.release()
+            return torch.stack(frames)
+        if backend == 'decord':
+            try:
+                import decord
+            except ImportError as e:
+                raise ImportError("video_decode_backend='decord' needs the decord package; set it to 'opencv' "
+                                  "(processing_video.py:96-109 reads the same frame indices)") from e
+            decord.bridge.set_bridge('torch')
+            vr = decord.VideoReader(path, ctx=decord.cpu(0))
+            return vr.get_batch(np.linspace(0, len(vr) - 1, vc.num_frames, dtype=int))
+        raise NotImplementedError(f"video_decode_backend={backend!r}: 'opencv' and 'decord' are built (the pytorchvideo "
+                                  f"branch re-samples in time inside a third-party transform)")
+
+    def transform(self, frames, hflip=None):
+        from . import ops
+        _need_cuda(type(self).__name__)
+        if hflip is None:                     # RandomHorizontalFlipVideo(p = 0.5): torch's RNG, as torchvision draws it
+            hflip = bool(torch.rand(1).item() < 0.5)
+        f = frames.contiguous().cuda(non_blocking=True)
+        out = torch.empty((3, f.shape[0], self.size, self.size), device=f.device, dtype=torch.float32)
+        return ops.video_preprocess(f, out, self.size, OPENAI_DATASET_MEAN, OPENAI_DATASET_STD, hflip)
+
+    def one(self, item):
+        return self.transform(self.decode_frames(item))
 
 
-class LanguageBindAudioProcessor(_Processor):
+def kaldi_mel_banks(num_bins, sample_freq=16000.0, padded=512, low_freq=20.0, high_freq=0.0):
+    """The triangular mel filters of torchaudio.compliance.kaldi.get_mel_banks (no VTLN) + the zero Nyquist column fbank
+    appends: float32 [num_bins, padded / 2 + 1].  Parameter-space work, done once per processor."""
+    nyq = 0.5 * sample_freq
+    if high_freq <= 0.0:
+        high_freq += nyq
+    mel = lambda f: 1127.0 * math.log(1.0 + f / 700.0)      # noqa: E731
+    nfft = padded // 2
+    lo, hi = mel(low_freq), mel(high_freq)
+    delta = (hi - lo) / (num_bins + 1)
+    b = torch.arange(num_bins, dtype=torch.float32).unsqueeze(1)
+    left, center, right = lo + b * delta, lo + (b + 1.0) * delta, lo + (b + 2.0) * delta
+    m = 1127.0 * (1.0 + (sample_freq / padded) * torch.arange(nfft, dtype=torch.float32) / 700.0).log().unsqueeze(0)
+    w = torch.max(torch.zeros(1), torch.min((m - left) / (center - left), (right - m) / (right - center)))
+    return torch.nn.functional.pad(w, (0, 1)).contiguous()
+
+
+class LanguageBindAudioProcessor(_ClipProcessor):
     modality = "audio"
+
+    def load(self, path):
+        """-> (float32 [channels, n], sample rate), as torchaudio.load (processing_audio.py:21-22)."""
+        if isinstance(path, tuple):
+            return path
+        import torchaudio
+        return torchaudio.load(path)
+
+    def transform(self, wave_and_sr, offsets=None):
+        """AudioTransform.__call__ (processing_audio.py:45-94) -> CUDA float32 [3, num_mel_bins, target_length]."""
+        from . import ops
+        _need_cuda(type(self).__name__)
+        vc = self.config.vision_config
+        wave, sr = wave_and_sr
+        if sr != vc.audio_sample_rate:
+            import torchaudio                                          # :49-51 (sinc resampling: third party, kept as is)
+            wave = torchaudio.functional.resample(wave, orig_freq=sr, new_freq=vc.audio_sample_rate)
+        if vc.audio_sample_rate != 16000:
+            raise NotImplementedError("the fbank kernel is built for 16 kHz (400 / 160 / 512-sample frames), the "
+                                      "reference's audio_sample_rate default (configuration_audio.py:206)")
+        wave = wave.to(torch.float32).contiguous().cuda(non_blocking=True)
+        key = (int(vc.num_mel_bins), str(wave.device))
+        cache = self.__dict__.setdefault('_mel', {})
+        if key not in cache:
+            cache[key] = kaldi_mel_banks(int(vc.num_mel_bins), float(vc.audio_sample_rate)).to(wave.device)
+        target = int(vc.target_length)
+        nf = int(ops.lib().missm_fbank_num_frames(wave.shape[1]))
+        if offsets is None:
+            offsets = (0, 0, 0)
+            if nf > target:                   # three random chunks: front / middle / back thirds (:57-77), numpy's RNG
+                import numpy as np
+                ranges = np.array_split(list(range(0, nf - target + 1)), 3)
+                if len(ranges[1]) == 0:
+                    ranges[1] = [0]
+                if len(ranges[2]) == 0:
+                    ranges[2] = [0]
+                offsets = tuple(int(np.random.choice(r)) for r in ranges)
+        out, _ = ops.audio_fbank(wave, cache[key], target, offsets, float(vc.audio_mean), float(vc.audio_std))
+        return out
+
+    def one(self, item):
+        return self.transform(self.load(item))
 
 
 transform_dict = {

@@ -376,6 +376,60 @@ def image_preprocess(src, out, S, mean, std, *, antialias, pre_div=255.0, clip_l
     return out
 
 
+class VideoArgs(ctypes.Structure):
+    """Mirror of `missm_video_args`."""
+    _fields_ = [("src", ctypes.c_void_p), ("dst", ctypes.c_void_p), ("T", ctypes.c_int32), ("H", ctypes.c_int32),
+                ("W", ctypes.c_int32), ("S", ctypes.c_int32), ("hflip", ctypes.c_int32),
+                ("mean", ctypes.c_float * 3), ("std_", ctypes.c_float * 3)]
+
+
+def video_preprocess(frames, out, S, mean, std, hflip=False):
+    """frames: CUDA uint8 [T, H, W, 3] (decoded RGB frames of one clip) -> out: CUDA float32 [3, T, S, S]."""
+    assert frames.is_cuda and frames.dtype == torch.uint8 and frames.dim() == 4 and frames.shape[3] == 3
+    frames = frames.contiguous()
+    T, H, W = frames.shape[:3]
+    assert out.is_cuda and out.is_contiguous() and out.dtype == F32 and tuple(out.shape) == (3, T, S, S)
+    a = VideoArgs()
+    a.src, a.dst, a.T, a.H, a.W, a.S, a.hflip = frames.data_ptr(), out.data_ptr(), T, H, W, S, int(bool(hflip))
+    a.mean, a.std_ = (ctypes.c_float * 3)(*mean), (ctypes.c_float * 3)(*std)
+    check(lib().missm_video_preprocess(ctypes.byref(a), stream_ptr()), "video_preprocess")
+    return out
+
+
+class FbankArgs(ctypes.Structure):
+    """Mirror of `missm_fbank_args`."""
+    _fields_ = [("wave", ctypes.c_void_p), ("wave_all", ctypes.c_void_p), ("n_samples", ctypes.c_int64),
+                ("n_total", ctypes.c_int64), ("mel_weights", ctypes.c_void_p), ("mel", ctypes.c_void_p),
+                ("wave_sum", ctypes.c_void_p), ("out", ctypes.c_void_p), ("n_mel", ctypes.c_int32),
+                ("target", ctypes.c_int32), ("offsets", ctypes.c_int32 * 3), ("mean", ctypes.c_float),
+                ("std_", ctypes.c_float)]
+
+
+def audio_fbank(wave_all, mel_weights, target, offsets, mean, std, out=None):
+    """wave_all: CUDA float32 [channels, n] as torchaudio.load returns it (at the model's sample rate) -> CUDA float32
+    [3, n_mel, target] (kaldi fbank of channel 0 after subtracting the mean of the whole tensor, chunk offsets
+    `offsets` (frames), (x - mean) / (2 std)).  Returns (out, n_frames)."""
+    assert wave_all.is_cuda and wave_all.dtype == F32 and wave_all.dim() == 2 and wave_all.is_contiguous()
+    n_mel = mel_weights.shape[0]
+    assert mel_weights.is_cuda and mel_weights.dtype == F32 and mel_weights.is_contiguous() and mel_weights.shape[1] == 257
+    n = wave_all.shape[1]
+    nf = int(lib().missm_fbank_num_frames(n))
+    if nf <= 0:
+        raise ValueError(f"audio of {n} samples is shorter than one 25 ms frame")
+    dev = wave_all.device
+    mel = torch.empty((nf, n_mel), device=dev, dtype=F32)
+    wsum = torch.empty((1,), device=dev, dtype=torch.float64)
+    if out is None:
+        out = torch.empty((3, n_mel, target), device=dev, dtype=F32)
+    a = FbankArgs()
+    a.wave, a.wave_all, a.n_samples, a.n_total = wave_all.data_ptr(), wave_all.data_ptr(), n, wave_all.numel()
+    a.mel_weights, a.mel, a.wave_sum, a.out = mel_weights.data_ptr(), mel.data_ptr(), wsum.data_ptr(), out.data_ptr()
+    a.n_mel, a.target, a.mean, a.std_ = n_mel, target, mean, std
+    a.offsets = (ctypes.c_int32 * 3)(*[int(o) for o in offsets])
+    check(lib().missm_audio_fbank(ctypes.byref(a), stream_ptr()), "audio_fbank")
+    return out, nf
+
+
 # ------------------------------------------------------------------- fp32 verification mode
 # (MISSM_PRECISION=fp32; csrc/fp32_mode.cu)  Not a performance path: every GEMM expands both fp32 operands into
 # six bf16 pieces along the contraction dimension and runs ONE tcgen05 bf16 GEMM over K' = 6 K.
