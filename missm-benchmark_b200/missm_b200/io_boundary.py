@@ -231,8 +231,9 @@ class LanguageBindVideoProcessor(_ClipProcessor):
     def transform(self, frames, hflip=None):
         from . import ops
         _need_cuda(type(self).__name__)
-        if hflip is None:                     # RandomHorizontalFlipVideo(p = 0.5): torch's RNG, as torchvision draws it
-            hflip = bool(torch.rand(1).item() < 0.5)
+        if hflip is None:                     # RandomHorizontalFlipVideo(p = 0.5) draws from Python's `random` module
+            import random
+            hflip = random.random() < 0.5
         f = frames.contiguous().cuda(non_blocking=True)
         out = torch.empty((3, f.shape[0], self.size, self.size), device=f.device, dtype=torch.float32)
         return ops.video_preprocess(f, out, self.size, OPENAI_DATASET_MEAN, OPENAI_DATASET_STD, hflip)

@@ -28,7 +28,8 @@ def test_video_transform_matches_reference_chain(gold, name):
     from missm_b200.io_boundary import LanguageBindVideoProcessor
     proc = LanguageBindVideoProcessor(_vcfg(video_decode_backend='opencv', num_frames=2))
     frames = gold[f"video/{name}/frames"]
-    torch.manual_seed(gold[f"video/{name}/seed"])                 # the processor draws the flip as torchvision does
+    import random
+    random.seed(gold[f"video/{name}/seed"])                       # the processor draws the flip as torchvision does
     out = proc.one(frames)
     assert out.is_cuda and tuple(out.shape) == (3, 2, 224, 224)
     want = gold[f"video/{name}/out_every2nd_pixel"]
@@ -67,12 +68,19 @@ def test_audio_fbank_vs_torchaudio_fresh_waveforms():
         ref = torchaudio.compliance.kaldi.fbank(wave - wave.mean(), htk_compat=True, sample_frequency=16000, use_energy=False,
                                                 window_type="hanning", num_mel_bins=112, dither=0.0, frame_length=25,
                                                 frame_shift=10)
+        ref64 = torchaudio.compliance.kaldi.fbank((wave - wave.mean()).double(), htk_compat=True, sample_frequency=16000,
+                                                  use_energy=False, window_type="hanning", num_mel_bins=112, dither=0.0,
+                                                  frame_length=25, frame_shift=10)
         T = ref.shape[0]
         out, nf = ops.audio_fbank(wave.cuda(), w, T, (0, 0, 0), 0.0, 0.5)      # mean 0, 2 * std = 1: the raw log-mel
         assert nf == T
-        err = (out[0].t().cpu() - ref).abs().max().item()
-        print(n, T, err)
-        assert err < 5e-4
+        mine = out[0].t().cpu()
+        err, err64, ta64 = (mine - ref).abs().max().item(), (mine.double() - ref64).abs().max().item(), \
+            (ref.double() - ref64).abs().max().item()
+        print(f"n {n} frames {T}: vs torchaudio fp32 {err:.2e}; vs its float64 run: this kernel {err64:.2e}, torchaudio fp32 {ta64:.2e}")
+        # raw log-mel values: two fp32 spectra (400-term DFT here, torch's FFT there) differ by their own rounding;
+        # the kernel must be as close to the float64 result as torchaudio's fp32 run is (x 3), and within 3e-3 of it
+        assert err < 3e-3 and err64 < max(5e-4, 3 * ta64)
     with pytest.raises(ValueError):
         ops.audio_fbank(torch.zeros(1, 100).cuda(), w, 10, (0, 0, 0), 0.0, 0.5)
 

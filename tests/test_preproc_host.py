@@ -68,6 +68,25 @@ def test_processors_keep_the_reference_surface_and_have_no_cpu_path():
         if not torch.cuda.is_available():
             with pytest.raises(RuntimeError, match="no CPU fallback"):
                 proc.transform(np.zeros((8, 8, 3), np.uint8))
-    for m in ('video', 'audio'):
-        with pytest.raises(NotImplementedError):
-            lb.transform_dict[m](cfg)("x.mp4")
+    # video / audio: host decode with the reference's own decoders, everything after it on the device -- no CPU path
+    vproc, aproc = lb.transform_dict['video'](cfg), lb.transform_dict['audio'](cfg)
+    for proc in (vproc, aproc):
+        assert hasattr(proc, 'batch_decode') and hasattr(proc, 'decode') and proc.config is cfg
+        with pytest.raises(ValueError):
+            proc()
+    with pytest.raises(ValueError):
+        vproc.decode_frames(torch.zeros(2, 3, 8, 8))                   # not uint8 [T, H, W, 3]
+    if not torch.cuda.is_available():
+        with pytest.raises(RuntimeError, match="no CPU fallback"):
+            vproc.transform(torch.zeros(2, 8, 8, 3, dtype=torch.uint8))
+        with pytest.raises(RuntimeError, match="no CPU fallback"):
+            aproc.transform((torch.zeros(1, 16000), 16000))
+
+
+def test_kaldi_mel_banks_equal_torchaudio():
+    """The mel filterbank handed to the fbank kernel is torchaudio's own (get_mel_banks + the zero Nyquist column)."""
+    torchaudio = pytest.importorskip("torchaudio")
+    from missm_b200.io_boundary import kaldi_mel_banks
+    for nb in (112, 128, 23):
+        ref, _ = torchaudio.compliance.kaldi.get_mel_banks(nb, 512, 16000.0, 20.0, 0.0, 100.0, -500.0, 1.0)
+        assert torch.equal(kaldi_mel_banks(nb), torch.nn.functional.pad(ref, (0, 1)))
