@@ -150,6 +150,8 @@ gemm_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
 
   // (p.num_m_blk counts 256-row pair tiles here)
 
+  if (warp < 4) {
+  reg_dealloc<56>();          // control warpgroup (TMA, MMA, TMEM allocator, spare): gives its registers away
   if (warp == 0) {
     // ================================ TMA producer (both CTAs) ========================
     int stage = 0;
@@ -264,7 +266,9 @@ gemm_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
         if (++acc == 2) acc = 0, acc_phase ^= 1;
       }
     }
-  } else if (warp >= 4) {
+  }
+  } else {
+    reg_alloc<224>();           // the two epilogue warpgroups take them
     // ================================ epilogue (both CTAs, own 128 rows) ==============
     const int q = warp & 3;
     const int half = (warp - 4) >> 2;
@@ -286,26 +290,30 @@ gemm_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
       const int m_blk = tile / p.num_n_blk, n_blk = tile % p.num_n_blk;
       const int row0 = m_blk * 256 + static_cast<int>(rank) * 128 + q * 32;
       // in-place RESID (aux_in aliases C): this warp's tile is only ever touched by this warp, and its
-      // loads are issued before its stores
-      uint4 aux[8], aux_next[8];
-      if constexpr (epilogue_has_aux<EPI>()) epilogue_aux_load<EPI>(p, row0, n_blk * BN + half * 32, lane, aux);
+      // loads are issued before its stores.
+      // ALL auxiliary tiles of this warp (residual / pre-activation / position rows of its BN / 64 chunks) are
+      // requested up front, before the accumulator is even complete: with one chunk of look-ahead the warp sat on
+      // the global-load latency of every chunk (ncu: the staging store of the aux tile was the top stall, out-proj
+      // ran at 2.4 TB/s of epilogue traffic) -- an epilogue warp needs its whole tile's bytes in flight.
+      constexpr int NCH = BN / 32 / (kEpiWarps / 4);
+      uint4 aux[NCH][8];
+      if constexpr (epilogue_has_aux<EPI>()) {
+#pragma unroll
+        for (int i = 0; i < NCH; ++i)
+          epilogue_aux_load<EPI>(p, row0, n_blk * BN + (half + i * (kEpiWarps / 4)) * 32, lane, aux[i]);
+      }
       mbar_wait(&tfull_bar[acc], acc_phase);
       tc_fence_after();
       const uint32_t t_row = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * BN;
-#pragma unroll 1
-      for (int c = half; c < BN / 32; c += kEpiWarps / 4) {
-        const int col0 = n_blk * BN + c * 32;
-        if (col0 >= p.N) break;  // warp-uniform
-        uint32_t r[32];
-        tmem_ld_32x32b_x32(t_row + c * 32, r);
-        if constexpr (epilogue_has_aux<EPI>()) {
-          if (c + kEpiWarps / 4 < BN / 32) epilogue_aux_load<EPI>(p, row0, col0 + (kEpiWarps / 4) * 32, lane, aux_next);
-        }
-        tmem_ld_wait();
-        if (row0 < p.M) epilogue_chunk<EPI, OUT_F32>(p, row0, col0, r, aux, stage, lane);   // warp-uniform
-        if constexpr (epilogue_has_aux<EPI>()) {
 #pragma unroll
-          for (int i = 0; i < 8; ++i) aux[i] = aux_next[i];
+      for (int i = 0; i < NCH; ++i) {
+        const int c = half + i * (kEpiWarps / 4);
+        const int col0 = n_blk * BN + c * 32;
+        if (col0 < p.N) {  // warp-uniform
+          uint32_t r[32];
+          tmem_ld_32x32b_x32(t_row + c * 32, r);
+          tmem_ld_wait();
+          if (row0 < p.M) epilogue_chunk<EPI, OUT_F32>(p, row0, col0, r, aux[i], stage, lane);   // warp-uniform
         }
       }
       tc_fence_before();

@@ -150,6 +150,18 @@ __device__ __forceinline__ void warp_store_tile32_bf16(uint32_t stage, int lane,
   __syncwarp();
 }
 
+// Register rebalancing between warpgroups (setmaxnreg): a kernel launched with 384 threads gets 65536 / 384 = 170
+// registers per thread; the producer / MMA warps need ~40, so the epilogue warpgroups can take up to 232 and keep
+// every auxiliary tile of a warp in flight at once.  Must be executed by ALL four warps of a warpgroup.
+template <int N>
+__device__ __forceinline__ void reg_dealloc() {
+  asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(N));
+}
+template <int N>
+__device__ __forceinline__ void reg_alloc() {
+  asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(N));
+}
+
 // ----------------------------------------------------------------------------------------
 // mbarrier
 // ----------------------------------------------------------------------------------------
