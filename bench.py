@@ -276,7 +276,7 @@ def run_gpu_arm(a):
     import torch
     import torch.distributed as dist
     import restatement as R                     # only for synthetic inputs/weights + the CPU baseline leg
-    from missm_b200 import ops, shapes
+    from missm_b200 import dist_utils, ops, shapes
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -315,7 +315,7 @@ def run_gpu_arm(a):
     B = a.batch if a.batch > 0 else cf['batch']
     host = R.synth_inputs(MODALS, B, cfgs, tcfg, seed=rank)
     host = {m: {k: t.pin_memory() for k, t in v.items()} for m, v in host.items()}
-    mi_host = R.synth_missing_index(B, a.missing, MODALS, seed=2025 + rank).pin_memory()
+    mi_host = R.synth_missing_index(B, a.missing, MODALS, seed=dist_utils.rank_seed(2025, rank)).pin_memory()
     labels_host = (torch.arange(B) % 3).pin_memory()
     data = {m: {k: t.to(dev) for k, t in v.items()} for m, v in host.items()}
     mi, labels = mi_host.to(dev), labels_host.to(dev)
@@ -324,7 +324,7 @@ def run_gpu_arm(a):
     code_of = {'language': 1, 'video': 2, 'audio': 3, 'image': 4, 'depth': 5, 'thermal': 6}
     # forward GFLOP of the samples the towers actually run (mask compaction skips the missing ones)
     fwd_gflop_step = sum(FWD_GFLOP[m] * int((mi_host != code_of[m]).sum()) for m in MODALS)
-    sweep_host = [R.synth_missing_index(B, r, MODALS, seed=2025 + rank).pin_memory() for r in SWEEP]
+    sweep_host = [R.synth_missing_index(B, r, MODALS, seed=dist_utils.rank_seed(2025, rank)).pin_memory() for r in SWEEP]
     sweep_dev = [t.to(dev) for t in sweep_host]
     if not train:
         fwd_gflop_step = sum(FWD_GFLOP[m] * int((t != code_of[m]).sum()) for t in sweep_host for m in MODALS)
@@ -383,10 +383,7 @@ def run_gpu_arm(a):
         host_ms[0] = (time.perf_counter() - h0 - (_bank.HOST_WAIT_S[0] - w0)) * 1e3 / steps
         e1.record()
         barrier()
-        ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
-        if world > 1:
-            dist.all_reduce(ms, op=dist.ReduceOp.MAX)          # max over ranks, device-timed
-        return float(ms)
+        return dist_utils.max_over_ranks(e0.elapsed_time(e1), device=dev)      # device-timed, max over ranks
 
     for _ in range(max(a.warmup, 3)):
         step_resident()
