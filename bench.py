@@ -305,12 +305,18 @@ def run_gpu_arm(a):
     model.train(train)
     net = model
     if world > 1 and train:
-        # train_ddp.py:189 (broadcast_buffers=True, find_unused_parameters=False, default gradient copies).
-        # MISSM_BENCH_BUCKET_VIEW=1 is a measurement switch only (gradient_as_bucket_view=True: no per-parameter
-        # copies into / out of the all-reduce buckets), reported in config.ddp
-        bucket_view = os.environ.get("MISSM_BENCH_BUCKET_VIEW") is not None
+        # The literal call of train_ddp.py:189.  The package's DDP integration switch (MISSM_DDP_BUCKET_VIEW, see
+        # missm_b200/ddp_integration.py and INTEGRATION.md) is ON by default here, as a deployment would set it:
+        # the unchanged call then defaults to gradient_as_bucket_view=True.  MISSM_DDP_BUCKET_VIEW=0 measures the
+        # stock reducer; MISSM_BENCH_BUCKET_MB is a measurement switch (bucket_cap_mb).  Both are reported in config.ddp.
+        if os.environ.get("MISSM_DDP_BUCKET_VIEW", "1") == "1":
+            from missm_b200 import ddp_integration
+            ddp_integration.install()
+        extra = {}
+        if os.environ.get("MISSM_BENCH_BUCKET_MB"):
+            extra["bucket_cap_mb"] = int(os.environ["MISSM_BENCH_BUCKET_MB"])
         net = torch.nn.parallel.DistributedDataParallel(model, device_ids=[local], broadcast_buffers=True,
-                                                        find_unused_parameters=False, gradient_as_bucket_view=bucket_view)
+                                                        find_unused_parameters=False, **extra)
 
     B = a.batch if a.batch > 0 else cf['batch']
     host = R.synth_inputs(MODALS, B, cfgs, tcfg, seed=rank)
@@ -468,7 +474,10 @@ def run_gpu_arm(a):
             "config": {"workload": WORKLOAD, "batch_per_gpu": B, "missing_ratio": a.missing,
                        "missing_samples": n_missing, "fusion": "sum", "layers": a.layers, "tower_streams": bool(model.encoder.tower_streams),
                        "ddp": (None if world == 1 or not train else "DistributedDataParallel as train_ddp.py:189" +
-                               (" + gradient_as_bucket_view (measurement switch)" if os.environ.get("MISSM_BENCH_BUCKET_VIEW") else "")),
+                               (" + MISSM_DDP_BUCKET_VIEW=1 (package switch: gradient_as_bucket_view defaults to True)"
+                                if os.environ.get("MISSM_DDP_BUCKET_VIEW", "1") == "1" else " (stock reducer)") +
+                               (f" + bucket_cap_mb={os.environ['MISSM_BENCH_BUCKET_MB']} (measurement switch)"
+                                if os.environ.get("MISSM_BENCH_BUCKET_MB") else "")),
                        "host_issue_ms_per_step": host_issue_ms, "binding_calls_per_step": binding_calls,
                        "variant": "; ".join(variant) if variant else None,
                        "baseline_config_index": a.config,

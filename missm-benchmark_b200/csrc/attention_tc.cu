@@ -73,7 +73,7 @@ struct AttnFwdSmem {
 
 __device__ __forceinline__ void fw_named_sync() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
 
-__global__ void __launch_bounds__(FW_THREADS, 1)
+__global__ void __maxnreg__(kCoResidentRegs)   // FW_THREADS threads, one CTA per SM
 attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm128, const __grid_constant__ CUtensorMap tm16,
                    const AttnFwdTcParams p) {
   extern __shared__ uint8_t smem_raw[];
@@ -103,9 +103,12 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm128, const __grid_const
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = sh->tmem_base;
-
+  // register pool of the CTA = 384 x kCoResidentRegs: control warpgroup (TMA, MMA, the two odd-row warps) 104, the two
+  // softmax warpgroups 184 (128 x 104 + 256 x 184 <= 384 x 160)
   const int n_full = p.sw / 128, n_rem16 = (p.sw % 128) / 16;
 
+  if (warp < 4) {
+  reg_dealloc<104>();
   if (warp == 0) {
     // ================================ TMA producer ====================================
     uint32_t it = 0, tcount = 0;
@@ -197,7 +200,7 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm128, const __grid_const
       __syncwarp();
       if (lane == 0) fw_trace(p, 0, tr, 5, tc);
     }
-  } else if (warp < 4) {
+  } else {
     // ========================= the odd row N-1 on the CUDA cores (warps 2 + 3) =========
     if (p.tail) {
       const int tw = warp - 2, t = tw * 32 + lane;
@@ -254,7 +257,9 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm128, const __grid_const
         }
       }
     }
-  } else if (warp >= 4) {
+  }
+  } else {
+    reg_alloc<184>();
     // ========================= softmax + output ========================================
     const int g = (warp - 4) >> 2;       // column half
     const int q = warp & 3;              // TMEM lane quarter

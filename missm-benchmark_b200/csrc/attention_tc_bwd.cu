@@ -172,7 +172,7 @@ __device__ __forceinline__ void store_rows64_bf16(uint32_t stage, int lane, cons
 // tm128 / tm16: [3D cols, N rows, n_seq] views of qkv with 64 x 128 and 64 x 16 boxes; td128 / td16:
 // the same for d_out (D cols).
 template <bool DKV>
-__global__ void __launch_bounds__(BW_THREADS, 1)
+__global__ void __maxnreg__(kCoResidentRegs)   // BW_THREADS threads, one CTA per SM
 attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm128, const __grid_constant__ CUtensorMap tm16,
                    const __grid_constant__ CUtensorMap td128, const __grid_constant__ CUtensorMap td16,
                    const AttnBwdTcParams p) {
@@ -209,12 +209,15 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm128, const __grid_const
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = sh->tmem_base;
-
+  // register pool of the CTA = 384 x kCoResidentRegs: control warpgroup 104, softmax warpgroups 184 (see attention_tc.cu)
   const int n_full = p.sw / 128;             // full 128-row boxes of a resident operand
   const int n_rem16 = (p.sw % 128) / 16;     // remaining 16-row boxes
   // column offsets (elements) of the operands inside a qkv row
   const int col_q = 0, col_k = p.D, col_v = 2 * p.D;
 
+  // register pool of the CTA = 384 x kCoResidentRegs: control warpgroup 104, softmax warpgroups 184 (see attention_tc.cu)
+  if (warp < 4) {
+  reg_dealloc<104>();
   if (warp == 0) {
     // ================================ TMA producer ====================================
     // (converged warp waits; one elected lane arms the barrier and issues the copies)
@@ -355,7 +358,7 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm128, const __grid_const
         cp.advance(p);
       }
     }
-  } else if (warp < 4) {
+  } else {
     // ===== warp 3: column statistics (DKV): -lse*log2e and delta per query;  warps 2 + 3: the odd row =====
     if constexpr (DKV) {
       auto load_stats = [&](uint32_t it, int item) {
@@ -425,7 +428,9 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm128, const __grid_const
         }
       }
     }
-  } else if (warp >= 4) {
+  }
+  } else {
+    reg_alloc<184>();
     // ========================= softmax warpgroups (one thread per row) =================
     const int g = (warp - 4) >> 2;       // warpgroup: takes the steps with n % 2 == g
     const int q = warp & 3;              // TMEM lane quarter

@@ -93,7 +93,7 @@ __device__ __forceinline__ void unit_decode(const GemmParams& p, int w, int& til
 }
 
 template <int BN, int EPI, bool OUT_F32, bool CLC>
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kGemmThreads, 1)
+__global__ void __cluster_dims__(2, 1, 1) __maxnreg__(kCoResidentRegs)   // kGemmThreads threads, one CTA per SM
 gemm_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                          const GemmParams p) {
   using Cfg = Gemm2Cfg<BN>;
@@ -268,7 +268,7 @@ gemm_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
     }
   }
   } else {
-    reg_alloc<224>();           // the two epilogue warpgroups take them
+    reg_alloc<208>();           // the two epilogue warpgroups take them (128 x 56 + 256 x 208 <= 384 x 160)
     // ================================ epilogue (both CTAs, own 128 rows) ==============
     const int q = warp & 3;
     const int half = (warp - 4) >> 2;

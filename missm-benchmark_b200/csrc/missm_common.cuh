@@ -153,6 +153,15 @@ __device__ __forceinline__ void warp_store_tile32_bf16(uint32_t stage, int lane,
 // Register rebalancing between warpgroups (setmaxnreg): a kernel launched with 384 threads gets 65536 / 384 = 170
 // registers per thread; the producer / MMA warps need ~40, so the epilogue warpgroups can take up to 232 and keep
 // every auxiliary tile of a warp in flight at once.  Must be executed by ALL four warps of a warpgroup.
+//
+// Co-residency budget: the persistent one-CTA-per-SM kernels are compiled for kCoResidentRegs registers per thread
+// (__maxnreg__), i.e. 384 x 160 = 61 440 of the SM's 65 536 registers, and rebalance INSIDE that pool.  The 4 096
+// registers left (and 128 of the 2 048 thread slots, > 1 KB of shared memory) admit one small foreign CTA per SM at any
+// time -- the per-parameter gradient copies of torch DDP's reducer and other 128-thread elementwise kernels -- which
+// otherwise could only start in the gaps between two persistent kernels: measured at 2 x B200, the reducer's stream
+// advanced ~12 launches per ms against ~18 needed, a third of the all-reduce buckets queued up behind it and ran
+// after the backward had finished (profiles/r03c_*).
+constexpr int kCoResidentRegs = 160;
 template <int N>
 __device__ __forceinline__ void reg_dealloc() {
   asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(N));

@@ -21,20 +21,8 @@ if _os.environ.get("MISSM_FUSED_ADAM", "0") == "1":
     from missm_b200 import optim as _optim
     _optim.install()
 
-# MISSM_DDP_BUCKET_VIEW=1: the unchanged train_ddp.py:189 (`DDP(model, device_ids=[local_rank], broadcast_buffers=True,
-# find_unused_parameters=False)`) then runs with gradient_as_bucket_view=True unless the call says otherwise: the
-# reducer stops copying every parameter's gradient into and out of its all-reduce buckets (~2 300 small launches and
-# 7 GB of traffic per step for the three-tower workload; measured at 2 x B200: 118.5 -> 115.8 ms / step).  Opt-in, as
-# above; `.grad` tensors then alias the buckets, which the script's optimizer / zero_grad handle as usual.
+# MISSM_DDP_BUCKET_VIEW=1: the unchanged train_ddp.py:189 then runs with gradient_as_bucket_view=True unless the call
+# says otherwise (missm_b200/ddp_integration.py; measured at 2 x B200: 1081 -> 1121 samples/s).  Opt-in, as above.
 if _os.environ.get("MISSM_DDP_BUCKET_VIEW", "0") == "1":
-    import functools as _functools
-    import torch.nn.parallel as _tnp
-
-    _ddp_init = _tnp.DistributedDataParallel.__init__
-
-    @_functools.wraps(_ddp_init)
-    def _init(self, *args, **kwargs):
-        kwargs.setdefault("gradient_as_bucket_view", True)
-        _ddp_init(self, *args, **kwargs)
-
-    _tnp.DistributedDataParallel.__init__ = _init
+    from missm_b200 import ddp_integration as _ddp
+    _ddp.install()

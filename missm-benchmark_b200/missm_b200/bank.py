@@ -96,6 +96,7 @@ class LanguageBind(nn.Module):
         self.modality_proj = nn.ModuleDict(self.modality_proj)
         self.compaction = os.environ.get("MISSM_COMPACTION", "1") != "0"
         self.tower_streams = os.environ.get("MISSM_TOWER_STREAMS", "1") != "0"
+        self.lockstep = os.environ.get("MISSM_LOCKSTEP", "1") != "0"
 
     @classmethod
     def from_models(cls, models, use_temp=True):
@@ -112,6 +113,7 @@ class LanguageBind(nn.Module):
         self.modality_encoder, self.modality_proj = nn.ModuleDict(enc), nn.ModuleDict(proj)
         self.compaction = os.environ.get("MISSM_COMPACTION", "1") != "0"
         self.tower_streams = os.environ.get("MISSM_TOWER_STREAMS", "1") != "0"
+        self.lockstep = os.environ.get("MISSM_LOCKSTEP", "1") != "0"
         return self
 
     def _side_streams(self, n, device):
@@ -169,35 +171,66 @@ class LanguageBind(nn.Module):
         use_streams = self.tower_streams and len(keys) > 1 and dev is not None
         main = torch.cuda.current_stream(dev) if use_streams else None
         streams = self._side_streams(len(keys), dev) if use_streams else None
-        for i, key in enumerate(keys):
+        # Lockstep issue (MISSM_LOCKSTEP=0 turns it off): the towers advance one encoder layer at a time in round-robin
+        # order, each on its own stream.  The GPU work is the same, but (a) every stream has work from the first
+        # microseconds of the step instead of after the host has issued the whole previous tower, and (b) autograd
+        # replays the backward in the reverse of this order -- layer 23 of every tower, then layer 22, ... -- which is
+        # the order the gradients really become ready in.  DDP (train_ddp.py:189) rebuilds its buckets after the first
+        # step in gradient-arrival order and launches bucket k+1 only after bucket k: with tower-by-tower issue the
+        # buckets of the second and third tower queued behind the FIRST layer of the first tower (ready at the very end
+        # of the backward), which left two thirds of the all-reduce exposed after the backward.
+        lockstep = self.lockstep and use_streams
+
+        def tower(i, key):
+            """Generator: the forward of tower i (yields between layers); returns its [B, P] output."""
             value = inputs[key]
             enc, proj = self.modality_encoder[key], self.modality_proj[key]
             scale = self._scale(key)
-            if use_streams:
-                streams[i].wait_stream(main)
-                ctx = torch.cuda.stream(streams[i])
-            else:
-                ctx = contextlib.nullcontext()
-            with ctx:
-                if mdev.type == 'cuda':
-                    value = {k: (t.to(mdev, non_blocking=True) if torch.is_tensor(t) and not t.is_cuda else t)
-                             for k, t in value.items()}
-                if key in plan:
-                    pidx, slot, n, B = plan[key]
-                    if n == 0:
-                        # only parameters that take a gradient (a peft-frozen ViT-L base would otherwise cost
-                        # 1.2 GB of zero-filled gradients that autograd throws away)
-                        params = [p for p in list(enc.parameters()) + list(proj.parameters()) if p.requires_grad]
-                        outputs[key] = _ZeroTower.apply(B, proj.weight.shape[0], proj.weight.device, *params)
-                    else:
-                        y = enc(**value, present_idx=pidx, n_present=n, proj=proj, scale=scale)[1]
-                        outputs[key] = ag.ScatterZeroFn.apply(y, slot, pidx, n, B)
+            if mdev.type == 'cuda':
+                value = {k: (t.to(mdev, non_blocking=True) if torch.is_tensor(t) and not t.is_cuda else t)
+                         for k, t in value.items()}
+            if key in plan:
+                pidx, slot, n, B = plan[key]
+                if n == 0:
+                    # only parameters that take a gradient (a peft-frozen ViT-L base would otherwise cost
+                    # 1.2 GB of zero-filled gradients that autograd throws away)
+                    params = [p for p in list(enc.parameters()) + list(proj.parameters()) if p.requires_grad]
+                    out = _ZeroTower.apply(B, proj.weight.shape[0], proj.weight.device, *params)
                 else:
-                    outputs[key] = enc(**value, proj=proj, scale=scale)[1]
-                if ddp_sms and outputs[key].requires_grad:
-                    outputs[key] = ag.BackwardSmsFn.apply(outputs[key], ddp_sms)
+                    y = (yield from enc.forward_steps(**value, present_idx=pidx, n_present=n, proj=proj,
+                                                      scale=scale))[1]
+                    out = ag.ScatterZeroFn.apply(y, slot, pidx, n, B)
+            else:
+                out = (yield from enc.forward_steps(**value, proj=proj, scale=scale))[1]
+            if ddp_sms and out.requires_grad:
+                out = ag.BackwardSmsFn.apply(out, ddp_sms)
+            return out
+
+        def on_stream(i):
             if use_streams:
-                outputs[key].record_stream(main)
+                return torch.cuda.stream(streams[i])
+            return contextlib.nullcontext()
+
+        if use_streams:
+            for st in streams:
+                st.wait_stream(main)
+        gens = {key: tower(i, key) for i, key in enumerate(keys)}
+        live = list(enumerate(keys))
+        while live:
+            still = []
+            for i, key in live:
+                with on_stream(i):
+                    try:
+                        if lockstep:
+                            next(gens[key])
+                            still.append((i, key))
+                        else:
+                            outputs[key] = T.run_steps(gens[key])
+                    except StopIteration as stop:
+                        outputs[key] = stop.value
+                if key in outputs and use_streams:
+                    outputs[key].record_stream(main)
+            live = still
         if use_streams:
             for st in streams:
                 main.wait_stream(st)

@@ -299,11 +299,16 @@ class CLIPVisionTransformer(nn.Module):
         self.post_layernorm = nn.LayerNorm(config.hidden_size, eps=config.layer_norm_eps)
         self._cache = {"embed": {}, "pool": {}}
 
-    def forward(self, pixel_values=None, output_attentions=None, output_hidden_states=None, return_dict=None,
-                present_idx=None, n_present=None, proj=None, scale=1.0):
+    def forward(self, *args, **kwargs):
         """Returns (last_hidden_state, pooled).  With `proj` (the bank's projection Linear) the pooled
         output is already projected, L2-normalised and scaled (fused tail, languagebind/__init__.py
         :79-83).  `present_idx`/`n_present`: run only these samples (mask compaction)."""
+        return run_steps(self.forward_steps(*args, **kwargs))
+
+    def forward_steps(self, pixel_values=None, output_attentions=None, output_hidden_states=None, return_dict=None,
+                      present_idx=None, n_present=None, proj=None, scale=1.0):
+        """`forward` as a generator that yields after the embedding and after every encoder layer, so that the
+        bank can issue the layers of several towers in lockstep (bank.LanguageBind.forward)."""
         if pixel_values is None:
             raise ValueError("You have to specify pixel_values")
         if output_attentions or output_hidden_states:
@@ -348,13 +353,24 @@ class CLIPVisionTransformer(nn.Module):
                 raise ValueError(f"{n_img} frames is not a multiple of num_frames={t}")
             temporal = ag.AttnMeta(H, cfg.layer_norm_eps, ops.SeqLayout.temporal(n_img // t, t, N),
                                    add_period=t, add_div=N)
+        yield
         for layer in self.encoder.layers:
             x = layer.run(x, spatial, temporal)
+            yield
         n_out = n_samp if not frames_in_batch else B
         T_pool = T
         rows = torch.arange(n_out * T_pool, device=x.device, dtype=torch.int32) * N
         pooled = _pool(self, x, rows, n_out, T_pool, self.post_layernorm, proj, scale, cfg.layer_norm_eps)
         return ModelOutput(x.view(n_img, N, D), pooled)
+
+
+def run_steps(gen):
+    """Drive a `forward_steps` generator to its end and hand back its return value."""
+    try:
+        while True:
+            next(gen)
+    except StopIteration as stop:
+        return stop.value
 
 
 def _pool(owner, x, rows, n_present, T, ln, proj, scale, eps):
@@ -385,9 +401,12 @@ class CLIPTextTransformer(nn.Module):
         self.final_layer_norm = nn.LayerNorm(config.hidden_size, eps=config.layer_norm_eps)
         self._cache = {"pool": {}}
 
-    def forward(self, input_ids=None, attention_mask=None, position_ids=None, output_attentions=None,
-                output_hidden_states=None, return_dict=None, present_idx=None, n_present=None, proj=None,
-                scale=1.0):
+    def forward(self, *args, **kwargs):
+        return run_steps(self.forward_steps(*args, **kwargs))
+
+    def forward_steps(self, input_ids=None, attention_mask=None, position_ids=None, output_attentions=None,
+                      output_hidden_states=None, return_dict=None, present_idx=None, n_present=None, proj=None,
+                      scale=1.0):
         if input_ids is None:
             raise ValueError("You have to specify input_ids")
         if position_ids is not None:
@@ -405,8 +424,10 @@ class CLIPTextTransformer(nn.Module):
                                  self.embeddings.position_embedding.weight)
         meta = ag.AttnMeta(cfg.num_attention_heads, cfg.layer_norm_eps, ops.SeqLayout.spatial(n_samp, L),
                            causal=True, key_mask=am, mask_rows=present_idx if am is not None else None)
+        yield
         for layer in self.encoder.layers:
             x = layer.run(x, meta, None)
+            yield
         rows = ops.argmax_rows(ids, sample_index=present_idx, n_samples=n_samp)
         pooled = _pool(self, x, rows, n_samp, 1, self.final_layer_norm, proj, scale, cfg.layer_norm_eps)
         return ModelOutput(None, pooled)
