@@ -24,8 +24,9 @@
 extern "C" {
 #endif
 
-#define MISSM_ABI_VERSION 7   /* 3: missm_set_persistent_sms; 4: fp32 verification mode; 5: missm_adam_multi;
-                                 6: missm_image_preprocess; 7: residual-block drivers, launch counter, GEMM profile */
+#define MISSM_ABI_VERSION 8   /* 3: missm_set_persistent_sms; 4: fp32 verification mode; 5: missm_adam_multi;
+                                 6: missm_image_preprocess; 7: residual-block drivers, launch counter, GEMM profile;
+                                 8: missm_patch_embed_implicit */
 
 int missm_version(void);
 const char* missm_last_error(void);
@@ -153,6 +154,16 @@ int missm_colsum_bf16(const void* x, int64_t ldx, int32_t M, int32_t N, float* p
  * -> bf16 [Bn * T * (H/ps) * (W/ps), Kpad], column (c*ps + i)*ps + j, zero padded */
 int missm_patchify(const float* pixels, const int32_t* sample_index, void* patches, int32_t Bn,
                    int32_t C, int32_t T, int32_t H, int32_t W, int32_t ps, int32_t Kpad, void* stream);
+/* The same convolution as an IMPLICIT GEMM on tcgen05 (csrc/patch_embed_tc.cu), forward only: reads the fp32 pixels
+ * directly (same addressing as missm_patchify), multiplies by w_bf16 [D, Kpad] (Conv2d weight flattened to (c, i, j),
+ * zero padded to Kpad), adds the position row and writes token rows -- what missm_patchify + missm_gemm_bf16 with
+ * MISSM_EPI_PATCH do, without the [rows, Kpad] im2col matrix:
+ *   tok[img * (P + 1) + 1 + patch, :] = patches(img, patch, :) . w^T + pos[1 + patch, :],  img = b * T + t, P = (H/ps)(W/ps)
+ * (row img * (P + 1) is the CLS row: missm_cls_rows).  Returns 0 if launched, -1 if the shape is not handled
+ * (ps != 14, Kpad > 640, D % 128 != 0): the caller then takes the explicit path. */
+int missm_patch_embed_implicit(const float* pixels, const int32_t* sample_index, const void* w_bf16, const float* pos,
+                               float* tok, int32_t Bn, int32_t C, int32_t T, int32_t H, int32_t W, int32_t ps,
+                               int32_t Kpad, int32_t D, void* stream);
 /* out[g] = sum of rows r of x f32 [M, D] with (r / div) % period == g  (temporal-embedding grad) */
 int missm_colsum_grouped_f32(const float* x, int32_t M, int32_t D, int32_t period, int32_t div,
                              float* out, void* stream);

@@ -347,7 +347,68 @@ extern "C" int missm_cast_f32_bf16(const float* src, int64_t ld_src, void* dst, 
   return 0;
 }
 
+// ---- small-footprint variant (default): 128 threads, <= 32 registers, no shared memory, so that a CTA fits into the
+// registers / thread slots / shared memory the persistent tcgen05 kernels leave free on every SM (kCoResidentRegs,
+// missm_common.cuh).  The pass is HBM-bound and the GEMMs of the other towers' streams are tensor-bound: co-resident,
+// it runs on bandwidth nobody else is using instead of waiting for a gap between two persistent kernels.
+// One thread = 8 columns (one 16-byte load per row), one CTA = 1024 columns x rows_per_block rows, no cross-thread
+// reduction at all: partial[blockIdx.y][col] is written straight from the accumulators.
+__global__ void __launch_bounds__(128, 16)
+colsum_bf16_small_kernel(const __nv_bfloat16* __restrict__ x, long ldx, int M, int N, float* __restrict__ partial,
+                         int rows_per_block) {
+  const int col0 = (blockIdx.x * 128 + threadIdx.x) * 8;
+  if (col0 >= N) return;
+  const int r0 = blockIdx.y * rows_per_block;
+  const int r1 = min(r0 + rows_per_block, M);
+  float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  const __nv_bfloat16* p = x + static_cast<long>(r0) * ldx + col0;
+  auto add = [&](const uint4& q) {
+    const float2 a = unpack_bf16x2(q.x), b = unpack_bf16x2(q.y), c = unpack_bf16x2(q.z), d = unpack_bf16x2(q.w);
+    acc[0] += a.x, acc[1] += a.y, acc[2] += b.x, acc[3] += b.y;
+    acc[4] += c.x, acc[5] += c.y, acc[6] += d.x, acc[7] += d.y;
+  };
+  int r = r0;
+  for (; r + 4 <= r1; r += 4, p += 4 * ldx) {      // four independent 16-byte loads in flight per thread
+    const uint4 q0 = *reinterpret_cast<const uint4*>(p);
+    const uint4 q1 = *reinterpret_cast<const uint4*>(p + ldx);
+    const uint4 q2 = *reinterpret_cast<const uint4*>(p + 2 * ldx);
+    const uint4 q3 = *reinterpret_cast<const uint4*>(p + 3 * ldx);
+    add(q0), add(q1), add(q2), add(q3);
+  }
+  for (; r < r1; ++r, p += ldx) add(*reinterpret_cast<const uint4*>(p));
+  float4* dst = reinterpret_cast<float4*>(partial + static_cast<long>(blockIdx.y) * N + col0);
+  dst[0] = make_float4(acc[0], acc[1], acc[2], acc[3]);
+  dst[1] = make_float4(acc[4], acc[5], acc[6], acc[7]);
+}
+// second stage, same footprint: a warp owns 8 columns x 4 row groups (32-byte row segments, the partials sit in L2),
+// two shuffles fold the row groups; fixed summation order
+__global__ void __launch_bounds__(128, 16)
+reduce_rows_small_kernel(const float* __restrict__ partial, int R, int N, float* __restrict__ out) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int c = blockIdx.x * 32 + warp * 8 + (lane & 7);
+  const int g = lane >> 3;
+  float s0 = 0.f, s1 = 0.f;
+  if (c < N) {
+    int r = g;
+    for (; r + 4 < R; r += 8) s0 += partial[static_cast<long>(r) * N + c], s1 += partial[static_cast<long>(r + 4) * N + c];
+    if (r < R) s0 += partial[static_cast<long>(r) * N + c];
+  }
+  float s = s0 + s1;
+  s += __shfl_xor_sync(0xffffffffu, s, 8);
+  s += __shfl_xor_sync(0xffffffffu, s, 16);
+  if (g == 0 && c < N) out[c] = s;
+}
+
+static bool colsum_small() {
+  static const bool on = getenv("MISSM_COLSUM_SMALL") == nullptr || atoi(getenv("MISSM_COLSUM_SMALL")) != 0;   // A/B switch
+  return on;
+}
 extern "C" int missm_colsum_num_partials(int32_t M) {
+  if (colsum_small()) {
+    int r = (M + 63) / 64;
+    if (r < 1) r = 1;
+    return r < 256 ? r : 256;
+  }
   int r = (M + 255) / 256;
   if (r < 1) r = 1;
   return r < 64 ? r : 64;
@@ -362,6 +423,14 @@ extern "C" int missm_colsum_bf16(const void* x, int64_t ldx, int32_t M, int32_t 
   }
   const int R = missm_colsum_num_partials(M);
   const int rows_per_block = (M + R - 1) / R;
+  if (colsum_small()) {
+    dim3 grid((N + 1023) / 1024, R);
+    colsum_bf16_small_kernel<<<grid, 128, 0, ST(stream)>>>(static_cast<const __nv_bfloat16*>(x), ldx, M, N, partial,
+                                                          rows_per_block); note_launch();
+    reduce_rows_small_kernel<<<(N + 31) / 32, 128, 0, ST(stream)>>>(partial, R, N, out); note_launch();
+    MISSM_CHECK_CUDA(cudaGetLastError());
+    return 0;
+  }
   dim3 grid((N + 255) / 256, R), block(32, kColsumRows);
   colsum_bf16_kernel<<<grid, block, 0, ST(stream)>>>(static_cast<const __nv_bfloat16*>(x), ldx, M, N,
                                                     partial, rows_per_block); note_launch();

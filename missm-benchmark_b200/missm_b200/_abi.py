@@ -7,7 +7,7 @@ I = ctypes.c_int32
 L = ctypes.c_int64
 F = ctypes.c_float
 
-ABI_VERSION = 7          # == MISSM_ABI_VERSION of include/missm_b200.h; _lib.lib() refuses a library built for another
+ABI_VERSION = 8          # == MISSM_ABI_VERSION of include/missm_b200.h; _lib.lib() refuses a library built for another
 
 # name -> argtypes (every function returns int32; 0 = ok)
 SIGNATURES = {
@@ -22,6 +22,7 @@ SIGNATURES = {
     "missm_colsum_num_partials": [I],
     "missm_colsum_bf16": [P, L, I, I, P, P, P],
     "missm_patchify": [P, P, P, I, I, I, I, I, I, I, P],
+    "missm_patch_embed_implicit": [P, P, P, P, P, I, I, I, I, I, I, I, I, P],
     "missm_colsum_grouped_f32": [P, I, I, I, I, P, P],
     "missm_copy_f32": [P, P, L, P],
     "missm_cls_rows": [P, P, P, I, I, I, P],

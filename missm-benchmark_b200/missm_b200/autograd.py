@@ -344,26 +344,38 @@ class VisionEmbedFn(torch.autograd.Function):
         Kpad = (K + 63) // 64 * 64          # whole 64-element K blocks: no TMA box of the GEMM leaves the tensor
         P = gh * gw
         wp = bf16_weight(cache, "patch", patch_w, cols_dst=Kpad)
-        patches = ops.patchify(pixels, ps, Kpad, T, sample_index=present_idx, n_samples=n_present)
         n_img = n_present * T
         tok = torch.empty((n_img * (P + 1), D), device=pixels.device, dtype=F32)
-        ops.gemm(patches, wp, out=tok, epilogue=EPI_PATCH, aux_in=pos.detach(), patch_P=P)
+        # implicit GEMM: the tcgen05 kernel gathers the patches from the fp32 image itself; the im2col matrix exists
+        # only in the backward, and only if the conv weight takes a gradient
+        patches = None
+        if not ops.patch_embed_implicit(pixels, wp, pos.detach(), tok, ps, T, sample_index=present_idx,
+                                        n_samples=n_present):
+            patches = ops.patchify(pixels, ps, Kpad, T, sample_index=present_idx, n_samples=n_present)
+            ops.gemm(patches, wp, out=tok, epilogue=EPI_PATCH, aux_in=pos.detach(), patch_P=P)
         ops.cls_rows(cls.detach(), pos.detach(), tok, n_img, P + 1)
         x0, mean, rstd = ops.layernorm_fwd(tok, ln_w, ln_b, eps, out_dtype=F32)
         ctx.dims = (n_img, P, D, K, tuple(patch_w.shape))
-        ctx.save_for_backward(tok, mean, rstd, patches, ln_w)
+        ctx.regather = None if patches is not None else (ps, Kpad, T, n_present)
+        ctx.save_for_backward(tok, mean, rstd, patches, ln_w, pixels if patches is None else None,
+                              present_idx if patches is None else None)
         return x0
 
     @staticmethod
     def backward(ctx, d_x0):
-        tok, mean, rstd, patches, ln_w = ctx.saved_tensors
+        tok, mean, rstd, patches, ln_w, pixels, present_idx = ctx.saved_tensors
         n_img, P, D, K, wshape = ctx.dims
         d_x0 = _contig(d_x0)
         _take_side(d_x0)
         d_tok, _, d_lnw, d_lnb, _ = ops.layernorm_bwd(d_x0, tok, mean, rstd, ln_w)
         d_pos, d_patch = ops.embed_bwd(d_tok, n_img, P + 1)
-        d_w = ops.gemm(d_patch, patches, a_mn=True, b_mn=True, out_dtype=F32)          # [D, Kpad]
-        d_w = d_w[:, :K].reshape(wshape)
+        d_w = None
+        if ctx.needs_input_grad[6]:
+            if patches is None:      # forward ran the implicit GEMM: gather the wgrad operand now
+                ps, Kpad, T, n_present = ctx.regather
+                patches = ops.patchify(pixels, ps, Kpad, T, sample_index=present_idx, n_samples=n_present)
+            d_w = ops.gemm(d_patch, patches, a_mn=True, b_mn=True, out_dtype=F32)          # [D, Kpad]
+            d_w = d_w[:, :K].reshape(wshape)
         d_cls = d_pos[0].clone()
         return None, None, None, None, None, d_cls, d_w, d_pos, d_lnw, d_lnb
 

@@ -244,6 +244,26 @@ def copy_f32(src, dst):
     return dst
 
 
+def patch_embed_implicit(pixels, w_bf16, pos, tok, ps, T=1, sample_index=None, n_samples=None):
+    """Patch-embedding conv as an implicit GEMM (csrc/patch_embed_tc.cu): fills the patch rows of `tok`
+    f32 [n_img * (P + 1), D] from pixels f32 [*, C, (T,) H, W], w_bf16 [D, Kpad] and pos f32 [P + 1, D].
+    Returns False if the library declines the shape (caller: patchify + gemm)."""
+    assert pixels.dtype == F32 and pixels.is_contiguous() and tok.dtype == F32 and pos.dtype == F32
+    assert pixels.dim() == (4 if T == 1 else 5)
+    C, H, W = pixels.shape[1], pixels.shape[-2], pixels.shape[-1]
+    Bn = n_samples if n_samples is not None else pixels.shape[0]
+    D, Kpad = w_bf16.shape
+    from . import _lib
+    _lib.CALLS[0] += 1
+    rc = lib().missm_patch_embed_implicit(_p(pixels), _p(sample_index), _p(w_bf16), _p(pos), _p(tok), Bn, C, T, H, W,
+                                          ps, Kpad, D, stream_ptr())
+    if rc == -1:
+        return False
+    if rc != 0:
+        check(rc, "patch_embed_implicit")
+    return True
+
+
 def cls_rows(cls, pos, tok, Bn, ntok):
     check(lib().missm_cls_rows(_p(cls), _p(pos), _p(tok), Bn, ntok, tok.shape[1], stream_ptr()), "cls_rows")
 

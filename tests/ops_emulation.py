@@ -337,6 +337,19 @@ def patchify(pixels, ps, Kpad, T=1, sample_index=None, n_samples=None):
     return patchify_f32(pixels, ps, Kpad, T, sample_index, n_samples).to(BF16)
 
 
+def patch_embed_implicit(pixels, w_bf16, pos, tok, ps, T=1, sample_index=None, n_samples=None):
+    """missm_patch_embed_implicit: tok[img * (P + 1) + 1 + patch] = patches(img, patch) . w^T + pos[1 + patch]."""
+    D, Kpad = w_bf16.shape
+    if ps != 14 or Kpad > 640 or D % 128:
+        return False
+    A = patchify(pixels, ps, Kpad, T, sample_index, n_samples)
+    P = pos.shape[0] - 1
+    n_img = A.shape[0] // P
+    v = (A.double() @ w_bf16.double().t()).float().view(n_img, P, D) + pos[1:].unsqueeze(0)
+    tok.view(n_img, P + 1, D)[:, 1:, :] = v
+    return True
+
+
 # ------------------------------------------------------------------ missm_image_preprocess (csrc/preprocess.cu)
 def _cubic_aa(x):
     a = -0.5
@@ -504,7 +517,7 @@ def block_mlp_bwd(st, d_out, d_out_bf16, colsum_given, wgrad):
 BLOCK_DRIVERS = {"attn_fwd": block_attn_fwd, "attn_bwd": block_attn_bwd, "mlp_fwd": block_mlp_fwd,
                  "mlp_bwd": block_mlp_bwd}
 
-BF16_MODE_OPS = ["attention_fwd", "attention_bwd", "cast_bf16", "colsum", "patchify"]
+BF16_MODE_OPS = ["attention_fwd", "attention_bwd", "cast_bf16", "colsum", "patchify", "patch_embed_implicit"]
 
 EMULATED_OPS = ["gemm", "expand6", "attention_f32_fwd", "attention_f32_bwd", "layernorm_fwd", "layernorm_bwd",
                 "gelu_f32_fwd", "gelu_f32_bwd", "colsum_grouped", "copy_f32", "patchify_f32", "cls_rows", "embed_bwd",

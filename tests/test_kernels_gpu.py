@@ -245,6 +245,48 @@ def test_cast_colsum_patchify(ops):
     assert torch.equal(pt[:, :588], ref.bfloat16()) and (pt[:, 588:] == 0).all()
 
 
+@pytest.mark.parametrize("case", ["image", "ragged", "video", "audio_grid"])
+def test_patch_embed_implicit_gemm(ops, case):
+    """The implicit-GEMM patch embedding (csrc/patch_embed_tc.cu: tcgen05 fed from the fp32 image, no im2col matrix)
+    against (a) the explicit path it replaces, patchify + GEMM with the EPI_PATCH epilogue, and (b) the fp32
+    convolution of the reference (Conv2d k = stride = 14, no bias, + position rows; modeling_video.py:29-51)."""
+    torch.manual_seed(11)
+    D, ps, Kpad = 256, 14, 640
+    T = 1
+    if case == "image":          # 3 gathered samples of 5, 224 x 224: 768 patches = 6 full tiles
+        px = torch.randn(5, 3, 224, 224, device=DEV)
+        idx, n = torch.tensor([4, 0, 2], device=DEV, dtype=torch.int32), 3
+    elif case == "ragged":       # 3 x 8 x 5 = 120 patches: one partial tile, no gather
+        px = torch.randn(3, 3, 112, 70, device=DEV)
+        idx, n = None, 3
+    elif case == "video":        # [B, C, T, H, W], 2 of 4 clips, 2 frames each
+        px = torch.randn(4, 3, 2, 56, 84, device=DEV)
+        idx, n, T = torch.tensor([3, 1], device=DEV, dtype=torch.int32), 2, 2
+    else:                        # the audio tower's 8 x 74 patch grid (112 x 1036 spectrogram), 2 samples
+        px = torch.randn(2, 3, 112, 1036, device=DEV)
+        idx, n = None, 2
+    H, W = px.shape[-2:]
+    P = (H // ps) * (W // ps)
+    w = torch.randn(D, 3, ps, ps, device=DEV) * 0.05
+    wb = ops.cast_bf16(w.reshape(D, -1), cols_dst=Kpad)
+    pos = torch.randn(P + 1, D, device=DEV)
+    n_img = n * T
+    tok = torch.full((n_img * (P + 1), D), 7.0, device=DEV)
+    assert ops.patch_embed_implicit(px, wb, pos, tok, ps, T, sample_index=idx, n_samples=n)
+    ref_tok = torch.full_like(tok, 7.0)
+    patches = ops.patchify(px, ps, Kpad, T, sample_index=idx, n_samples=n)
+    ops.gemm(patches, wb, out=ref_tok, epilogue=ops.EPI_PATCH, aux_in=pos, patch_P=P)
+    torch.cuda.synchronize()
+    # same bf16 operands, same K order, fp32 accumulation: the two tensor-core paths agree to rounding of the sum
+    assert rel(tok, ref_tok) < 1e-6, rel(tok, ref_tok)
+    assert torch.equal(tok.view(n_img, P + 1, D)[:, 0], torch.full((n_img, D), 7.0, device=DEV))     # CLS rows untouched
+    sel = px if idx is None else px[idx.long()]
+    if T > 1:
+        sel = sel.permute(0, 2, 1, 3, 4).reshape(n_img, 3, H, W)
+    conv = torch.nn.functional.conv2d(sel, w, stride=ps).flatten(2).transpose(1, 2) + pos[1:]
+    assert rel(tok.view(n_img, P + 1, D)[:, 1:], conv) < 6e-3
+
+
 def test_embed_pool_l2norm(ops):
     torch.manual_seed(7)
     B, ntok, D = 4, 9, 256
