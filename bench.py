@@ -474,7 +474,8 @@ def run_gpu_arm(a):
             "config": {"workload": WORKLOAD, "batch_per_gpu": B, "missing_ratio": a.missing,
                        "missing_samples": n_missing, "fusion": "sum", "layers": a.layers, "tower_streams": bool(model.encoder.tower_streams),
                        "ddp": (None if world == 1 or not train else "DistributedDataParallel as train_ddp.py:189" +
-                               (" + MISSM_DDP_BUCKET_VIEW=1 (package switch: gradient_as_bucket_view defaults to True)"
+                               (" + MISSM_DDP_BUCKET_VIEW=1 (package switch: gradient_as_bucket_view defaults to True, "
+                                 f"bucket_cap_mb to {os.environ.get('MISSM_DDP_BUCKET_MB', '200')})"
                                 if os.environ.get("MISSM_DDP_BUCKET_VIEW", "1") == "1" else " (stock reducer)") +
                                (f" + bucket_cap_mb={os.environ['MISSM_BENCH_BUCKET_MB']} (measurement switch)"
                                 if os.environ.get("MISSM_BENCH_BUCKET_MB") else "")),
