@@ -31,6 +31,12 @@ extern "C" {
 int missm_version(void);
 const char* missm_last_error(void);
 
+/* Select the co-resident variants of the persistent kernels (tcgen05 GEMM, attention forward / backward): compiled for
+ * 160 instead of 168 registers per thread, so that one 128-thread, <= 32-register foreign CTA (torch DDP's per-parameter
+ * gradient copies) fits on every SM while they run.  Costs ~1.6 % of a single-GPU step, gains more than that under
+ * DDP; the encoder bank turns it on when torch.distributed runs more than one rank.  MISSM_CORESIDENT=0/1 in the
+ * environment pins it. */
+int missm_set_coresident(int32_t on);
 /* SMs the persistent kernels (tcgen05 GEMM, tcgen05 attention: one CTA per SM) spread over from now on; n <= 0
  * restores the default (148, or MISSM_PERSISTENT_SMS).  Process-wide, read at every launch.  The host side lowers it
  * for the backward pass under data parallelism so that NCCL's all-reduce CTAs (issued by the unchanged script's DDP

@@ -64,8 +64,8 @@ struct AttnFwdSmem {
   uint64_t q_full[2], q_empty[2];
   uint64_t s_full, p_full, o_full, o_empty;
   uint32_t tmem_base;
-  float xmax[2][128];     // row max / row sum halves exchanged between the two warps of a row
-  float xsum[2][128];
+  float xmax[2][128];     // row max halves exchanged between the two warps of a row
+  float xsum[2][2][128];  // row sum halves, [tile parity][column half][row]: read one tile later, in the epilogue
   float tail_w[kTailW];         // odd row: P
   float tail_x[4];              //          max / sum halves of the two tail warps
   float tail_part[64];          //          partial output of warp 3
@@ -73,7 +73,8 @@ struct AttnFwdSmem {
 
 __device__ __forceinline__ void fw_named_sync() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
 
-__global__ void __maxnreg__(kCoResidentRegs)   // FW_THREADS threads, one CTA per SM
+template <bool CO>
+__global__ void MISSM_PERSISTENT_BOUNDS(CO)   // FW_THREADS threads, one CTA per SM
 attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm128, const __grid_constant__ CUtensorMap tm16,
                    const AttnFwdTcParams p) {
   extern __shared__ uint8_t smem_raw[];
@@ -108,7 +109,7 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm128, const __grid_const
   const int n_full = p.sw / 128, n_rem16 = (p.sw % 128) / 16;
 
   if (warp < 4) {
-  reg_dealloc<104>();
+  if constexpr (CO) reg_dealloc<104>();
   if (warp == 0) {
     // ================================ TMA producer ====================================
     uint32_t it = 0, tcount = 0;
@@ -259,7 +260,7 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm128, const __grid_const
     }
   }
   } else {
-    reg_alloc<184>();
+    if constexpr (CO) reg_alloc<184>();
     // ========================= softmax + output ========================================
     const int g = (warp - 4) >> 2;       // column half
     const int q = warp & 3;              // TMEM lane quarter
@@ -276,7 +277,7 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm128, const __grid_const
 
     // epilogue of a finished tile: O / l -> bf16 (this warp writes columns [g*32, g*32+32)), lse
     auto epilogue = [&](uint32_t tc, int item, int tile, float mx, float sum_own, bool has_rows) {
-      const float sum = sum_own + sh->xsum[g ^ 1][rloc];
+      const float sum = sum_own + sh->xsum[tc & 1][g ^ 1][rloc];
       mbar_wait(&sh->o_full, tc & 1);
       tc_fence_after();
       if (tracer) fw_trace(p, 1 + g, tr, 13, tc);
@@ -340,16 +341,18 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm128, const __grid_const
           }
         }
         sh->xmax[g][rloc] = mx;
-        sh->xsum[g][rloc] = prev_sum;          // the previous tile's partial row sum rides along
         if (tracer) fw_trace(p, 1 + g, tr, 12, tc);
-        fw_named_sync();
+        fw_named_sync();                        // (also orders the xsum of tile tc-1, written before its p_full arrive)
         mx = fmaxf(mx, sh->xmax[g ^ 1][rloc]);
-        // ---- previous tile: P V has finished meanwhile -> write its output
-        if (prev_item >= 0) epilogue(tc - 1, prev_item, prev_tile, prev_mx, prev_sum, prev_rows);
-        fw_named_sync();                        // xmax / xsum may be overwritten from here on
         if (tracer) fw_trace(p, 1 + g, tr, 15, tc);
-        // ---- pass 2: P = exp2(S*log2e - max*log2e) -> bf16 into the P region; partial row sum
-        //      (the P region is free: P V of the previous tile completed before o_full)
+        // ---- pass 2: P = exp2(S*log2e - max*log2e) -> bf16 into the P region; partial row sum.
+        //      The P region is free once P V of the previous tile has completed (o_full).  The epilogue below waits for
+        //      the same phase again, which returns at once: phase tc of o_full cannot complete before every softmax
+        //      thread has arrived on o_empty, i.e. has passed that second wait.
+        if (prev_item >= 0) {
+          mbar_wait(&sh->o_full, (tc - 1) & 1);
+          tc_fence_after();
+        }
         const float mx2 = mx * kLog2eFw;
         float sum = 0.f;
         if (has_rows) {
@@ -387,15 +390,20 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm128, const __grid_const
           }
           tmem_st_wait();
         }
+        sh->xsum[tc & 1][g][rloc] = sum;       // read by the other half's warp in the epilogue of this tile, one bar.sync later
         tc_fence_before();
         mbar_arrive(&sh->p_full);
         if (tracer) fw_trace(p, 1 + g, tr, 16, tc);
+        // ---- previous tile's output while the MMA warp computes S of the next tile (S is single-buffered: the
+        //      softmax warps used to sit idle here for ~1.6 k of every ~8 k cycles).  Its P V finished long ago; the
+        //      other half's row sum was published before that warp's p_full arrive of tile tc-1 and ordered by the
+        //      bar.sync of this iteration.
+        if (prev_item >= 0) epilogue(tc - 1, prev_item, prev_tile, prev_mx, prev_sum, prev_rows);
         prev_item = item, prev_tile = t, prev_mx = mx, prev_sum = sum, prev_rows = has_rows;
       }
     }
     // ---- the last tile of this CTA
     if (prev_item >= 0) {
-      sh->xsum[g][rloc] = prev_sum;
       fw_named_sync();
       epilogue(tc - 1, prev_item, prev_tile, prev_mx, prev_sum, prev_rows);
     }
@@ -431,7 +439,8 @@ int attention_fwd_tc(const missm_attn_args* a, cudaStream_t stream) {
   const int smem = 4 * FW_KV_BYTES + 2 * FW_TILE_BYTES + 8 * 2048 + static_cast<int>(sizeof(AttnFwdSmem)) + 1024;
   static bool configured = false;
   if (!configured) {
-    MISSM_CHECK_CUDA(cudaFuncSetAttribute(attn_fwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    MISSM_CHECK_CUDA(cudaFuncSetAttribute(attn_fwd_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    MISSM_CHECK_CUDA(cudaFuncSetAttribute(attn_fwd_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     configured = true;
   }
   const int grid = p.n_items < persistent_sms() ? p.n_items : persistent_sms();
@@ -442,7 +451,7 @@ int attention_fwd_tc(const missm_attn_args* a, cudaStream_t stream) {
     MISSM_CHECK_CUDA(cudaMalloc(&d, nb));
     MISSM_CHECK_CUDA(cudaMemsetAsync(d, 0, nb, stream));
     p.trace = d;
-    attn_fwd_tc_kernel<<<grid, FW_THREADS, smem, stream>>>(tm128, tm16, p); note_launch();
+    attn_fwd_tc_kernel<false><<<grid, FW_THREADS, smem, stream>>>(tm128, tm16, p); note_launch();
     MISSM_CHECK_CUDA(cudaStreamSynchronize(stream));
     long long* h = static_cast<long long*>(malloc(nb));
     MISSM_CHECK_CUDA(cudaMemcpy(h, d, nb, cudaMemcpyDeviceToHost));
@@ -455,7 +464,11 @@ int attention_fwd_tc(const missm_attn_args* a, cudaStream_t stream) {
     cudaFree(d);
     return 0;
   }
-  attn_fwd_tc_kernel<<<grid, FW_THREADS, smem, stream>>>(tm128, tm16, p); note_launch();
+  if (coresident())
+    attn_fwd_tc_kernel<true><<<grid, FW_THREADS, smem, stream>>>(tm128, tm16, p);
+  else
+    attn_fwd_tc_kernel<false><<<grid, FW_THREADS, smem, stream>>>(tm128, tm16, p);
+  note_launch();
   MISSM_CHECK_CUDA(cudaGetLastError());
   return 0;
 }

@@ -171,8 +171,8 @@ __device__ __forceinline__ void store_rows64_bf16(uint32_t stage, int lane, cons
 
 // tm128 / tm16: [3D cols, N rows, n_seq] views of qkv with 64 x 128 and 64 x 16 boxes; td128 / td16:
 // the same for d_out (D cols).
-template <bool DKV>
-__global__ void __maxnreg__(kCoResidentRegs)   // BW_THREADS threads, one CTA per SM
+template <bool DKV, bool CO>
+__global__ void MISSM_PERSISTENT_BOUNDS(CO)   // BW_THREADS threads, one CTA per SM
 attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm128, const __grid_constant__ CUtensorMap tm16,
                    const __grid_constant__ CUtensorMap td128, const __grid_constant__ CUtensorMap td16,
                    const AttnBwdTcParams p) {
@@ -217,7 +217,7 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm128, const __grid_const
 
   // register pool of the CTA = 384 x kCoResidentRegs: control warpgroup 104, softmax warpgroups 184 (see attention_tc.cu)
   if (warp < 4) {
-  reg_dealloc<104>();
+  if constexpr (CO) reg_dealloc<104>();
   if (warp == 0) {
     // ================================ TMA producer ====================================
     // (converged warp waits; one elected lane arms the barrier and issues the copies)
@@ -430,7 +430,7 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm128, const __grid_const
     }
   }
   } else {
-    reg_alloc<184>();
+    if constexpr (CO) reg_alloc<184>();
     // ========================= softmax warpgroups (one thread per row) =================
     const int g = (warp - 4) >> 2;       // warpgroup: takes the steps with n % 2 == g
     const int q = warp & 3;              // TMEM lane quarter
@@ -670,8 +670,10 @@ int attention_bwd_tc(const missm_attn_args* a, cudaStream_t stream) {
   const int smem = 4 * BW_RES_BYTES + 4 * BW_TILE_BYTES + 4 * BW_STAT * 4 + 8 * 2048 + static_cast<int>(sizeof(AttnBwdSmem)) + 1024;
   static bool configured = false;
   if (!configured) {
-    MISSM_CHECK_CUDA(cudaFuncSetAttribute(attn_bwd_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    MISSM_CHECK_CUDA(cudaFuncSetAttribute(attn_bwd_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    MISSM_CHECK_CUDA(cudaFuncSetAttribute(attn_bwd_tc_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    MISSM_CHECK_CUDA(cudaFuncSetAttribute(attn_bwd_tc_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    MISSM_CHECK_CUDA(cudaFuncSetAttribute(attn_bwd_tc_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    MISSM_CHECK_CUDA(cudaFuncSetAttribute(attn_bwd_tc_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     configured = true;
   }
   const int grid = p.n_items < persistent_sms() ? p.n_items : persistent_sms();
@@ -692,9 +694,9 @@ int attention_bwd_tc(const missm_attn_args* a, cudaStream_t stream) {
     p.trace = d;
     launch_delta(0);
     p.tail = 0, p.nt = (a->N + 127) / 128;     // tracing walks all tiles
-    attn_bwd_tc_kernel<true><<<grid, BW_THREADS, smem, stream>>>(tm128, tm16, td128, td16, p); note_launch();
+    attn_bwd_tc_kernel<true, false><<<grid, BW_THREADS, smem, stream>>>(tm128, tm16, td128, td16, p); note_launch();
     p.trace = d + 3 * 330 * 3;
-    attn_bwd_tc_kernel<false><<<grid, BW_THREADS, smem, stream>>>(tm128, tm16, td128, td16, p); note_launch();
+    attn_bwd_tc_kernel<false, false><<<grid, BW_THREADS, smem, stream>>>(tm128, tm16, td128, td16, p); note_launch();
     MISSM_CHECK_CUDA(cudaStreamSynchronize(stream));
     long long* h = static_cast<long long*>(malloc(nb));
     MISSM_CHECK_CUDA(cudaMemcpy(h, d, nb, cudaMemcpyDeviceToHost));
@@ -712,8 +714,13 @@ int attention_bwd_tc(const missm_attn_args* a, cudaStream_t stream) {
   // DQ: its odd QUERY row is computed by warps 2-3 of the kernel itself
   AttnBwdTcParams pk = p;
   pk.tail = 0;
-  attn_bwd_tc_kernel<true><<<grid, BW_THREADS, smem, stream>>>(tm128, tm16, td128, td16, pk); note_launch();
-  attn_bwd_tc_kernel<false><<<grid, BW_THREADS, smem, stream>>>(tm128, tm16, td128, td16, p); note_launch();
+  if (coresident()) {
+    attn_bwd_tc_kernel<true, true><<<grid, BW_THREADS, smem, stream>>>(tm128, tm16, td128, td16, pk); note_launch();
+    attn_bwd_tc_kernel<false, true><<<grid, BW_THREADS, smem, stream>>>(tm128, tm16, td128, td16, p); note_launch();
+  } else {
+    attn_bwd_tc_kernel<true, false><<<grid, BW_THREADS, smem, stream>>>(tm128, tm16, td128, td16, pk); note_launch();
+    attn_bwd_tc_kernel<false, false><<<grid, BW_THREADS, smem, stream>>>(tm128, tm16, td128, td16, p); note_launch();
+  }
   MISSM_CHECK_CUDA(cudaGetLastError());
   return 0;
 }

@@ -219,6 +219,15 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA,
 static thread_local char g_last_error[512] = "";
 
 static std::atomic<int> g_persistent_sms_override{0};
+// co-resident variants of the persistent kernels (missm_common.cuh: kCoResidentRegs); MISSM_CORESIDENT=0/1 pins it
+static std::atomic<int> g_coresident{0};
+bool coresident() {
+  static const int pinned = [] {
+    const char* e = getenv("MISSM_CORESIDENT");
+    return e ? (atoi(e) != 0 ? 1 : 0) : -1;
+  }();
+  return pinned >= 0 ? pinned != 0 : g_coresident.load(std::memory_order_relaxed) != 0;
+}
 
 int persistent_sms() {
   static const int v = [] {
@@ -398,6 +407,10 @@ extern "C" int missm_gemm_bf16(const missm_gemm_args* a, void* stream_v) {
 
 extern "C" int missm_version(void) { return MISSM_ABI_VERSION; }
 extern "C" const char* missm_last_error(void) { return g_last_error; }
+extern "C" int missm_set_coresident(int32_t on) {
+  g_coresident.store(on != 0, std::memory_order_relaxed);
+  return 0;
+}
 extern "C" int missm_set_persistent_sms(int32_t n) {
   if (n < 2 || n > kNumSMs) n = 0;
   g_persistent_sms_override.store(n & ~1, std::memory_order_relaxed);

@@ -92,8 +92,8 @@ __device__ __forceinline__ void unit_decode(const GemmParams& p, int w, int& til
   kb1 = kb0 + p.kblk_per_split < p.num_kblk ? kb0 + p.kblk_per_split : p.num_kblk;
 }
 
-template <int BN, int EPI, bool OUT_F32, bool CLC>
-__global__ void __cluster_dims__(2, 1, 1) __maxnreg__(kCoResidentRegs)   // kGemmThreads threads, one CTA per SM
+template <int BN, int EPI, bool OUT_F32, bool CLC, bool CO>
+__global__ void __cluster_dims__(2, 1, 1) MISSM_PERSISTENT_BOUNDS(CO)   // kGemmThreads threads, one CTA per SM
 gemm_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                          const GemmParams p) {
   using Cfg = Gemm2Cfg<BN>;
@@ -268,7 +268,7 @@ gemm_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
     }
   }
   } else {
-    reg_alloc<208>();           // the two epilogue warpgroups take them (128 x 56 + 256 x 208 <= 384 x 160)
+    reg_alloc<CO ? 208 : 224>();           // the two epilogue warpgroups take them (128 x 56 + 256 x 208 <= 384 x 160)
     // ================================ epilogue (both CTAs, own 128 rows) ==============
     const int q = warp & 3;
     const int half = (warp - 4) >> 2;
@@ -332,11 +332,11 @@ gemm_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
   }
 }
 
-template <int BN, int EPI, bool OUT_F32, bool CLC>
-static int launch_gemm2_sched(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmParams& p, int grid,
-                              cudaStream_t stream) {
+template <int BN, int EPI, bool OUT_F32, bool CLC, bool CO>
+static int launch_gemm2_co(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmParams& p, int grid,
+                           cudaStream_t stream) {
   using Cfg = Gemm2Cfg<BN>;
-  auto kern = gemm_tcgen05_2cta_kernel<BN, EPI, OUT_F32, CLC>;
+  auto kern = gemm_tcgen05_2cta_kernel<BN, EPI, OUT_F32, CLC, CO>;
   static bool configured = false;  // benign race: the attribute call is idempotent
   if (!configured) {
     MISSM_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
@@ -345,6 +345,12 @@ static int launch_gemm2_sched(const CUtensorMap& tmA, const CUtensorMap& tmB, co
   kern<<<grid, kGemmThreads, Cfg::SMEM_BYTES, stream>>>(tmA, tmB, p); note_launch();
   MISSM_CHECK_CUDA(cudaGetLastError());
   return 0;
+}
+template <int BN, int EPI, bool OUT_F32, bool CLC>
+static int launch_gemm2_sched(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmParams& p, int grid,
+                              cudaStream_t stream) {
+  if (coresident()) return launch_gemm2_co<BN, EPI, OUT_F32, CLC, true>(tmA, tmB, p, grid, stream);
+  return launch_gemm2_co<BN, EPI, OUT_F32, CLC, false>(tmA, tmB, p, grid, stream);
 }
 // grid < 0: dynamic schedule, one cluster per work unit (-grid CTAs)
 template <int BN, int EPI, bool OUT_F32>

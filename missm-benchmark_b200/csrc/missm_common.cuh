@@ -162,6 +162,12 @@ __device__ __forceinline__ void warp_store_tile32_bf16(uint32_t stage, int lane,
 // advanced ~12 launches per ms against ~18 needed, a third of the all-reduce buckets queued up behind it and ran
 // after the backward had finished (profiles/r03c_*).
 constexpr int kCoResidentRegs = 160;
+// Every persistent kernel exists in both variants (template parameter CO): the co-resident one costs ~1.6 % of a
+// single-GPU step (fewer registers for the epilogue / softmax warps), so it is selected at run time -- by
+// missm_set_coresident(1), which the encoder bank calls when torch.distributed runs more than one rank.
+constexpr int kFullRegs = 168;          // 65 536 / 384 threads, rounded down to the allocation unit
+bool coresident();                      // gemm_tcgen05.cu
+#define MISSM_PERSISTENT_BOUNDS(CO) __maxnreg__((CO) ? kCoResidentRegs : kFullRegs)
 template <int N>
 __device__ __forceinline__ void reg_dealloc() {
   asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(N));

@@ -40,6 +40,7 @@ SIGNATURES = {
     "missm_fusion_sum_fwd": [P, P],
     "missm_fusion_sum_bwd": [P, P, P, P, P, P],
     "missm_set_persistent_sms": [I],
+    "missm_set_coresident": [I],
     "missm_expand6_bf16": [P, L, I, I, P, L, I, I, I, P],
     "missm_patchify_f32": [P, P, P, I, I, I, I, I, I, I, P],
     "missm_gelu_f32_fwd": [P, P, L, P],

@@ -9,7 +9,7 @@ import os
 import torch  # noqa: F401  (loads libcudart into the process before our library)
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(os.path.dirname(_HERE), "lib", "libmissm_b200.so")
+LIB_PATH = os.environ.get("MISSM_LIB_PATH") or os.path.join(os.path.dirname(_HERE), "lib", "libmissm_b200.so")   # (override: A/B builds)
 
 c_void_p = ctypes.c_void_p
 c_int = ctypes.c_int32

@@ -45,6 +45,21 @@ def _ddp_backward_sms():
     return int(os.environ.get("MISSM_DDP_SMS", "0"))
 
 
+_CORESIDENT = [None]
+
+
+def _coresident_policy():
+    """The persistent kernels run in their co-resident variants (include/missm_b200.h: missm_set_coresident) when the
+    process is one rank of several: DDP's reducer (train_ddp.py:189) then issues a small copy kernel per parameter
+    gradient while the backward is running, and those must not wait for the gaps between two one-CTA-per-SM kernels
+    (profiles/r03c_*, r03e_* timelines).  Alone on the GPU the full-register variants are ~1.6 % faster."""
+    import torch.distributed as dist
+    want = bool(dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1)
+    if _CORESIDENT[0] != want:
+        ops.set_coresident(want)
+        _CORESIDENT[0] = want
+
+
 def _require_cuda_index(mi, mdev):
     """missing_index on the host is uploaded when the model lives on a CUDA device; there is no CPU path."""
     if not mi.is_cuda:
@@ -140,6 +155,9 @@ class LanguageBind(nn.Module):
         """inputs: {modal: {'pixel_values': ...} | {'input_ids', 'attention_mask'}} -> {modal: [B, P]}.
         `missing_index` (int64 [B], optional) enables compaction: a tower only runs the samples whose
         code differs from its own; rows of missing samples come back as zeros."""
+        mdev = self._param_device()
+        if mdev.type == 'cuda':
+            _coresident_policy()
         policy = _ddp_backward_sms()
         if policy:
             ops.set_persistent_sms(0)          # forward (also the no_grad evaluation after an epoch): all SMs

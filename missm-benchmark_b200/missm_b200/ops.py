@@ -23,6 +23,11 @@ def set_persistent_sms(n):
     check(lib().missm_set_persistent_sms(int(n)), "set_persistent_sms")
 
 
+def set_coresident(on):
+    """Co-resident variants of the persistent kernels on / off (include/missm_b200.h: missm_set_coresident)."""
+    check(lib().missm_set_coresident(int(bool(on))), "set_coresident")
+
+
 def _p(t):
     return ctypes.c_void_p(t.data_ptr()) if t is not None else None
 
