@@ -92,26 +92,40 @@ patch_embed_tc_kernel(const __grid_constant__ CUtensorMap tmB, const PatchEmbedP
       sts128(sA_u + kb_pad0 * A_STAGE_BYTES + i * 16, make_uint4(0u, 0u, 0u, 0u));
     __syncthreads();
     const int items = pp.C * PS * BM;                        // (channel, kernel row) x tile row
-    for (int w = threadIdx.x; w < items; w += PE_THREADS) {
-      const int m_local = w & (BM - 1), ci = w >> 7;
-      const int row = m0 + m_local;
-      if (row >= p.M) continue;
-      const int img = row / pp.P, patch = row - img * pp.P;
-      const int py = patch / pp.gw, pxi = patch - py * pp.gw;
-      const int c = ci / PS, i = ci - c * PS;
-      const int b = img / pp.T, t = img - b * pp.T;
-      const long src_b = pp.sample_index ? pp.sample_index[b] : b;
-      const float2* src = reinterpret_cast<const float2*>(
-          pp.px + (((src_b * pp.C + c) * pp.T + t) * pp.H + (py * PS + i)) * static_cast<long>(pp.W) + pxi * PS);
-      float2 v[PS / 2];
+    // three work items per thread and iteration: 21 independent 8-byte loads in flight (the gather is latency-bound;
+    // with one item per iteration a 128-patch tile took 21 DRAM round trips)
+    constexpr int UN = 3;
+    for (int w0 = threadIdx.x; w0 < items; w0 += UN * PE_THREADS) {
+      float2 v[UN][PS / 2];
+      int m_loc[UN], k0s[UN];
 #pragma unroll
-      for (int j = 0; j < PS / 2; ++j) v[j] = __ldg(src + j);
-      const int k0 = ci * PS;
-      const uint32_t row_off = sA_u + m_local * 128;
+      for (int u = 0; u < UN; ++u) {
+        const int w = w0 + u * PE_THREADS;
+        const int m_local = w & (BM - 1), ci = w >> 7;
+        const int row = m0 + m_local;
+        m_loc[u] = (w < items && row < p.M) ? m_local : -1;
+        k0s[u] = ci * PS;
+        if (m_loc[u] < 0) continue;
+        const int img = row / pp.P, patch = row - img * pp.P;
+        const int py = patch / pp.gw, pxi = patch - py * pp.gw;
+        const int c = ci / PS, i = ci - c * PS;
+        const int b = img / pp.T, t = img - b * pp.T;
+        const long src_b = pp.sample_index ? pp.sample_index[b] : b;
+        const float2* src = reinterpret_cast<const float2*>(
+            pp.px + (((src_b * pp.C + c) * pp.T + t) * pp.H + (py * PS + i)) * static_cast<long>(pp.W) + pxi * PS);
 #pragma unroll
-      for (int j = 0; j < PS / 2; ++j) {
-        const int k = k0 + 2 * j, kb = k >> 6, kk = k & 63;
-        sts32(row_off + kb * A_STAGE_BYTES + (((kk >> 3) ^ (m_local & 7)) << 4) + (kk & 7) * 2, pack_bf16x2(v[j].x, v[j].y));
+        for (int j = 0; j < PS / 2; ++j) v[u][j] = __ldg(src + j);
+      }
+#pragma unroll
+      for (int u = 0; u < UN; ++u) {
+        if (m_loc[u] < 0) continue;
+        const uint32_t row_off = sA_u + m_loc[u] * 128;
+#pragma unroll
+        for (int j = 0; j < PS / 2; ++j) {
+          const int k = k0s[u] + 2 * j, kb = k >> 6, kk = k & 63;
+          sts32(row_off + kb * A_STAGE_BYTES + (((kk >> 3) ^ (m_loc[u] & 7)) << 4) + (kk & 7) * 2,
+                pack_bf16x2(v[u][j].x, v[u][j].y));
+        }
       }
     }
     fence_proxy_async_smem();          // generic-proxy stores -> visible to the tensor core's async proxy
