@@ -24,9 +24,9 @@
 extern "C" {
 #endif
 
-#define MISSM_ABI_VERSION 8   /* 3: missm_set_persistent_sms; 4: fp32 verification mode; 5: missm_adam_multi;
+#define MISSM_ABI_VERSION 9   /* 3: missm_set_persistent_sms; 4: fp32 verification mode; 5: missm_adam_multi;
                                  6: missm_image_preprocess; 7: residual-block drivers, launch counter, GEMM profile;
-                                 8: missm_patch_embed_implicit */
+                                 8: missm_patch_embed_implicit; 9: missm_gemm_args.colsum_part */
 
 int missm_version(void);
 const char* missm_last_error(void);
@@ -84,9 +84,14 @@ typedef struct missm_gemm_args {
   int32_t force_bn;   /* 0 = auto, 128 or 256 = force tile N */
   float* colsum_out;  /* optional [N], PRE-ZEROED: += column sums over m of the fp32 value that is written
                          to C (bias gradient of the consumer layer, fused into the producing GEMM) */
+  float* colsum_part; /* optional [missm_gemm_colsum_rows(M), N] (v9): row r receives the column sums of C rows
+                         [32 r, 32 r + 32) -- of the values as STORED (rounded to bf16 when C is bf16) -- written with
+                         plain stores by the epilogue warp that owns those rows: deterministic, no atomics, no zeroing.
+                         Reduce the rows with missm_reduce_partials.  Not with split-K. */
 } missm_gemm_args;
 
 int missm_gemm_bf16(const missm_gemm_args* args, void* stream);
+int missm_gemm_colsum_rows(int32_t M);   /* rows of a colsum_part workspace: ceil(M / 32) */
 
 /* ---------------------------------------------------------------------------------------
  * Fused attention (head_dim 64).  Replaces transformers 4.3x CLIPAttention's score/softmax/

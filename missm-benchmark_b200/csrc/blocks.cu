@@ -127,13 +127,15 @@ int check_attn(const missm_attn_block_args* a) {
 
 int gemm(const void* A, int lda, bool a_mn, const void* B, int ldb, bool b_mn, void* C, int ldc, bool c_f32, int M, int N,
          int K, void* stream, int epi = MISSM_EPI_LINEAR, const float* bias = nullptr, const void* aux_in = nullptr,
-         int ld_aux_in = 0, void* aux_out = nullptr, int ld_aux_out = 0, int scale_cols = 0, float col_scale = 1.f) {
+         int ld_aux_in = 0, void* aux_out = nullptr, int ld_aux_out = 0, int scale_cols = 0, float col_scale = 1.f,
+         float* colsum_part = nullptr) {
   missm_gemm_args g;
   memset(&g, 0, sizeof(g));
   g.A = A, g.B = B, g.C = C, g.bias = bias, g.aux_in = aux_in, g.aux_out = aux_out;
   g.M = M, g.N = N, g.K = K, g.lda = lda, g.ldb = ldb, g.ldc = ldc, g.ld_aux_in = ld_aux_in, g.ld_aux_out = ld_aux_out;
   g.a_mn = a_mn, g.b_mn = b_mn, g.epilogue = epi, g.out_f32 = c_f32;
   g.scale_cols = scale_cols, g.col_scale = col_scale;
+  g.colsum_part = colsum_part;
   return missm_gemm_bf16(&g, stream);
 }
 
@@ -293,7 +295,9 @@ MlpScratch mlp_scratch(const missm_mlp_block_args* a, void* base) {
   MlpScratch s;
   s.dy = c.take<bf16>(M * D), s.d_u = c.take<bf16>(M * F), s.d_h = c.take<bf16>(M * D);
   s.ln_part = c.take<float>(static_cast<int64_t>(missm_ln_bwd_num_partials(a->M)) * 3 * D);
-  s.cs_part = c.take<float>(static_cast<int64_t>(missm_colsum_num_partials(a->M)) * (F > D ? F : D));
+  const int cs_rows = missm_colsum_num_partials(a->M) > missm_gemm_colsum_rows(a->M) ? missm_colsum_num_partials(a->M)
+                                                                                      : missm_gemm_colsum_rows(a->M);
+  s.cs_part = c.take<float>(static_cast<int64_t>(cs_rows) * (F > D ? F : D));
   s.bytes = c.off;
   return s;
 }
@@ -349,10 +353,17 @@ extern "C" int missm_mlp_block_bwd(const missm_mlp_block_args* a, void* stream) 
   }
   if (wg && !a->d_out_colsum_given) RC(missm_colsum_bf16(dy, D, M, D, w.cs_part, g.b2, stream));
   if (wg) RC(gemm(dy, D, true, s.act, F, true, g.w2, F, true, D, F, M, stream));                            // dY^T a
-  RC(gemm(dy, D, false, a->w2, F, true, w.d_u, F, false, M, F, D, stream, MISSM_EPI_DGELU, nullptr, s.u, F));  // (dY W2) gelu'(u)
+  // (dY W2) gelu'(u); its epilogue also leaves the column sums of every 32 rows of d_u (= the fc1 bias gradient after one
+  // small reduction): no second pass over the [M, F] gradient
+  static const bool fused_cs = getenv("MISSM_COLSUM_EPILOGUE") == nullptr || atoi(getenv("MISSM_COLSUM_EPILOGUE")) != 0;   // A/B
+  RC(gemm(dy, D, false, a->w2, F, true, w.d_u, F, false, M, F, D, stream, MISSM_EPI_DGELU, nullptr, s.u, F, nullptr, 0, 0, 1.f,
+          wg && fused_cs ? w.cs_part : nullptr));
   if (wg) {
+    if (fused_cs)
+      RC(missm_reduce_partials(w.cs_part, missm_gemm_colsum_rows(M), F, g.b1, F, 1.0f, stream));
+    else
+      RC(missm_colsum_bf16(w.d_u, F, M, F, w.cs_part, g.b1, stream));
     RC(gemm(w.d_u, F, true, s.h, D, true, g.w1, D, true, F, D, M, stream));                                 // d_u^T h
-    RC(missm_colsum_bf16(w.d_u, F, M, F, w.cs_part, g.b1, stream));
   }
   RC(gemm(w.d_u, F, false, a->w1, D, true, w.d_h, D, false, M, D, F, stream));                              // d_u W1
   RC(missm_layernorm_bwd(w.d_h, D, 1, a->x, D, nullptr, s.mean, s.rstd, a->ln_w, a->d_out, a->dx, a->dx_bf16, w.ln_part, g.ln_w,

@@ -28,6 +28,7 @@ struct GemmParams {
   int patch_P;
   int atomic_out;
   float* colsum_out;
+  float* colsum_part;    // [ceil(M / 32), N]: per-warp partial column sums of the stored values
   int stream_k;          // 1: every CTA (pair) owns one contiguous slice of the linearised (tile, k-block) space
   long sk_per_cta;       //    k-blocks per slice
 };
@@ -272,6 +273,20 @@ __device__ __forceinline__ void epilogue_chunk(const GemmParams& p, int row0, in
     }
     const float cs = warp_colsum32(v, lane);
     if (lane < ncols) atomicAdd(p.colsum_out + col0 + lane, cs);
+  }
+  if (p.colsum_part != nullptr) {   // warp-uniform
+    // column sums of this warp's 32 rows of the tile AS STORED (bf16-rounded when C is bf16), one coalesced 128-byte
+    // store per chunk into the row of the partial buffer that this warp owns: bias gradients without a second pass
+    // over C and without atomics
+    float t[32];
+#pragma unroll
+    for (int j = 0; j < 32; ++j) {
+      float x = v[j];
+      if constexpr (!OUT_F32) x = __bfloat162float(__float2bfloat16(x));
+      t[j] = (row0 + lane < p.M) ? x : 0.f;
+    }
+    const float cs = warp_colsum32(t, lane);
+    if (lane < ncols) p.colsum_part[static_cast<long>(row0 >> 5) * p.N + col0 + lane] = cs;
   }
   __syncwarp();
   if constexpr (EPI == MISSM_EPI_PATCH)

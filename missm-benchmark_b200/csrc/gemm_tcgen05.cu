@@ -407,6 +407,7 @@ extern "C" int missm_gemm_bf16(const missm_gemm_args* a, void* stream_v) {
 
 extern "C" int missm_version(void) { return MISSM_ABI_VERSION; }
 extern "C" const char* missm_last_error(void) { return g_last_error; }
+extern "C" int missm_gemm_colsum_rows(int32_t M) { return (M + 31) / 32; }
 extern "C" int missm_set_coresident(int32_t on) {
   g_coresident.store(on != 0, std::memory_order_relaxed);
   return 0;
@@ -441,6 +442,7 @@ static int gemm_bf16_impl(const missm_gemm_args* a, void* stream_v) {
   p.aux_out = a->aux_out, p.ld_aux_out = a->ld_aux_out;
   p.patch_P = a->patch_P;
   p.colsum_out = a->colsum_out;
+  p.colsum_part = a->colsum_part;
   p.stream_k = 0, p.sk_per_cta = 0;
   // large-M problems go to the CTA-pair kernel (gemm_tcgen05_2cta.cu); MISSM_GEMM_1CTA=1 keeps
   // everything on the single-CTA kernel (A/B measurements)
@@ -468,7 +470,7 @@ static int gemm_bf16_impl(const missm_gemm_args* a, void* stream_v) {
   const long tiles = static_cast<long>(p.num_m_blk) * p.num_n_blk;
   int splits = 1;
   const bool may_split = (epi == MISSM_EPI_LINEAR && a->out_f32 && a->bias == nullptr &&
-                          a->scale_cols == 0 && a->split_k != 1 && a->colsum_out == nullptr);
+                          a->scale_cols == 0 && a->split_k != 1 && a->colsum_out == nullptr && a->colsum_part == nullptr);
   if (may_split) {
     if (a->split_k > 1) {
       splits = a->split_k;

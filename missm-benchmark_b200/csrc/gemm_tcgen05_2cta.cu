@@ -400,7 +400,7 @@ int gemm_launch_2cta(const missm_gemm_args* a, GemmParams p, cudaStream_t stream
   const long tiles = static_cast<long>(p.num_m_blk) * p.num_n_blk;
   int splits = 1;
   const bool may_split = (a->epilogue == MISSM_EPI_LINEAR && a->out_f32 && a->bias == nullptr &&
-                          a->scale_cols == 0 && a->split_k != 1 && a->colsum_out == nullptr);
+                          a->scale_cols == 0 && a->split_k != 1 && a->colsum_out == nullptr && a->colsum_part == nullptr);
   if (may_split) {
     if (a->split_k > 1) {
       splits = a->split_k;

@@ -7,11 +7,12 @@ I = ctypes.c_int32
 L = ctypes.c_int64
 F = ctypes.c_float
 
-ABI_VERSION = 8          # == MISSM_ABI_VERSION of include/missm_b200.h; _lib.lib() refuses a library built for another
+ABI_VERSION = 9          # == MISSM_ABI_VERSION of include/missm_b200.h; _lib.lib() refuses a library built for another
 
 # name -> argtypes (every function returns int32; 0 = ok)
 SIGNATURES = {
     "missm_gemm_bf16": [P, P],
+    "missm_gemm_colsum_rows": [I],
     "missm_attention_fwd": [P, P],
     "missm_attention_bwd": [P, P],
     "missm_layernorm_fwd": [P, L, P, P, I, I, P, P, P, P, L, I, P, P, I, I, F, P],

@@ -44,7 +44,7 @@ class GemmArgs(ctypes.Structure):
         ("epilogue", c_int), ("out_f32", c_int),
         ("scale_cols", c_int), ("col_scale", c_float),
         ("patch_P", c_int), ("split_k", c_int), ("force_bn", c_int),
-        ("colsum_out", c_void_p),
+        ("colsum_out", c_void_p), ("colsum_part", c_void_p),
     ]
 
 

@@ -40,7 +40,7 @@ def _ld(t):
 # --------------------------------------------------------------------------------------- GEMM
 def gemm(a, b, *, a_mn=False, b_mn=False, out=None, out_dtype=BF16, bias=None,
          epilogue=EPI_LINEAR, aux_in=None, aux_out=None, scale_cols=0, col_scale=1.0,
-         patch_P=0, out_rows=None, split_k=0, force_bn=0, colsum_out=None):
+         patch_P=0, out_rows=None, split_k=0, force_bn=0, colsum_out=None, colsum_part=None):
     """C[m,n] = epilogue(sum_k A[m,k] B[n,k]).  `a`: [M,K] (or [K,M] if a_mn), `b`: [N,K]
     (or [K,N] if b_mn); both bf16 CUDA tensors, row-major.  `colsum_out` (f32 [N], pre-zeroed) receives
     the column sums of the fp32 values written to C (fused bias gradient)."""
@@ -71,6 +71,9 @@ def gemm(a, b, *, a_mn=False, b_mn=False, out=None, out_dtype=BF16, bias=None,
     if colsum_out is not None:
         assert colsum_out.dtype == F32 and colsum_out.numel() == N and colsum_out.is_contiguous()
         g.colsum_out = colsum_out.data_ptr()
+    if colsum_part is not None:      # f32 [ceil(M / 32), N]: per-32-row column sums of the stored values (no atomics)
+        assert colsum_part.dtype == F32 and colsum_part.is_contiguous() and tuple(colsum_part.shape) == ((M + 31) // 32, N)
+        g.colsum_part = colsum_part.data_ptr()
     check(lib().missm_gemm_bf16(ctypes.byref(g), stream_ptr()), "gemm_bf16")
     return out
 

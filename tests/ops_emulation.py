@@ -25,7 +25,7 @@ def _gelu_grad(x):
 # ------------------------------------------------------------------ missm_gemm_bf16 (bf16 operands, fp32 accumulate)
 def gemm(a, b, *, a_mn=False, b_mn=False, out=None, out_dtype=None, bias=None, epilogue=EPI_LINEAR, aux_in=None,
          aux_out=None, scale_cols=0, col_scale=1.0, patch_P=0, out_rows=None, split_k=0, force_bn=0,
-         colsum_out=None):
+         colsum_out=None, colsum_part=None):
     assert a.dtype == BF16 and b.dtype == BF16
     out_dtype = BF16 if out_dtype is None else out_dtype
     A = (a.t() if a_mn else a).double()

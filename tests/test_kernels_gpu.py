@@ -66,6 +66,12 @@ def test_gemm_epilogues(ops, M):
     dref = acc * (s * (1 + 1.702 * uu.float() * (1 - s)))
     assert rel(out, dref) < 4e-3
     assert rel(cs, dref.sum(0)) < 2e-5              # fused bias gradient (fp32 values, before the bf16 rounding)
+    # the deterministic variant: per-32-row column sums of the values AS STORED, written by the owning warp (no atomics)
+    part = torch.full(((M + 31) // 32, N), float("nan"), device=DEV)
+    out2 = ops.gemm(A, B, epilogue=ops.EPI_DGELU, aux_in=uu, colsum_part=part)
+    assert torch.equal(out2, out) and not torch.isnan(part).any()
+    ref_part = torch.nn.functional.pad(out2.float(), (0, 0, 0, (-M) % 32)).view(-1, 32, N).sum(1)
+    assert rel(part, ref_part) < 1e-6
     P = 100
     Bsz = M // P
     A, acc = A[:Bsz * P], acc[:Bsz * P]
