@@ -119,6 +119,45 @@ def _worker_model(rank, world, port, q, lora_r):
     dist.destroy_process_group()
 
 
+def _worker_ddp_switch(rank, world, port, q):
+    """MISSM_DDP_BUCKET_VIEW=1: importing the drop-in `languagebind` makes the UNCHANGED DDP call of train_ddp.py:189
+    default to bucket views and the larger bucket; an explicit keyword wins; gradients are those of the stock reducer."""
+    sys.path.insert(0, os.path.join(ROOT, "missm-benchmark_b200"))
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world),
+                      MISSM_DDP_BUCKET_VIEW="1", MISSM_DDP_BUCKET_MB="7")
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    import languagebind  # noqa: F401  (the switch is read at import)
+    from torch.nn.parallel import DistributedDataParallel as DDP
+    from src.model import baseline as B
+    args = types.SimpleNamespace(modality_types=['image', 'audio'], feature_dims=16, fusion_dim=8, dropout_prob=0.0)
+    out = {}
+
+    def run(make_ddp):
+        torch.manual_seed(0)
+        head = B.modal_concat(args, 3)
+        ddp = make_ddp(head)
+        opt = torch.optim.SGD(head.parameters(), lr=0.1)
+        g = torch.Generator().manual_seed(100 + rank)
+        for _ in range(3):          # zero_grad (set_to_none) -> forward -> backward -> step, as train_ddp.py:222-254
+            opt.zero_grad()
+            batch = {'image': torch.randn(4, 16, generator=g), 'audio': torch.randn(4, 16, generator=g)}
+            ddp(batch, torch.tensor([0, 4, 3, 0])).square().mean().backward()
+            opt.step()
+        return ddp, torch.cat([p.detach().flatten() for p in head.parameters()])
+
+    ddp, w_switch = run(lambda m: DDP(m, broadcast_buffers=True, find_unused_parameters=False))      # the script's call
+    out["bucket_view"] = bool(ddp.gradient_as_bucket_view)
+    out["bucket_bytes"] = int(ddp.bucket_bytes_cap)
+    ddp2, w_stock = run(lambda m: DDP(m, broadcast_buffers=True, find_unused_parameters=False,
+                                      gradient_as_bucket_view=False, bucket_cap_mb=25))
+    out["explicit_wins"] = (not ddp2.gradient_as_bucket_view) and int(ddp2.bucket_bytes_cap) == 25 * 1024 * 1024
+    out["same_weights"] = bool(torch.allclose(w_switch, w_stock, rtol=0, atol=1e-7))
+    out["weights"] = w_switch.tolist()
+    q.put((rank, out))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
 def _run_two_ranks(target, *extra):
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
@@ -131,6 +170,14 @@ def _run_two_ranks(target, *extra):
         p.join(timeout=120)
         assert p.exitcode == 0
     return res
+
+
+def test_two_rank_ddp_integration_switch():
+    res = _run_two_ranks(_worker_ddp_switch)
+    for r in (0, 1):
+        assert res[r]["bucket_view"] and res[r]["bucket_bytes"] == 7 * 1024 * 1024
+        assert res[r]["explicit_wins"] and res[r]["same_weights"]
+    assert res[0]["weights"] == res[1]["weights"]
 
 
 def test_two_rank_product_model_with_an_empty_tower():
