@@ -170,12 +170,17 @@ class LanguageBind(nn.Module):
         mdev = self._param_device()
         if missing_index is not None and self.compaction and len(keys) > 0:
             mi = missing_index.reshape(-1).to(torch.int64).contiguous()
+            mi_host = mi if not mi.is_cuda else None
             mi = _require_cuda_index(mi, mdev)
             codes = [MISSING_TYPE_INDEX.get(k, -1) for k in keys]
             idx, slot, counts = ops.compact_mask(mi, codes)
-            t0 = time.perf_counter()
-            counts = counts.tolist()          # the one host sync of the step: sizes of the towers' batches
-            HOST_WAIT_S[0] += time.perf_counter() - t0
+            if mi_host is not None:
+                # the index came from the host: the towers' batch sizes are counted there, no device read-back
+                counts = [int((mi_host != c).sum()) for c in codes]
+            else:
+                t0 = time.perf_counter()
+                counts = counts.tolist()      # the one host sync of the step: sizes of the towers' batches
+                HOST_WAIT_S[0] += time.perf_counter() - t0
             B = mi.numel()
             for i, k in enumerate(keys):
                 if counts[i] < B:

@@ -162,3 +162,20 @@ def test_synthetic_inputs_follow_the_loader_contract():
     ids, am = d['language']['input_ids'], d['language']['attention_mask']
     assert ids.shape == (3, 77) and ids.dtype == torch.int64 and am[:, :21].all() and not am[:, 21:].any()
     assert (ids.argmax(-1) == 20).all()                                     # first EOT
+
+
+def test_host_side_tower_batch_sizes_match_the_compaction_contract():
+    """When `missing_index` arrives on the host (the end-to-end call with pinned host buffers) the bank counts the
+    present samples per tower there instead of reading the kernel's counts back (one host sync less): the host count
+    must be exactly what missm_compact_mask reports (contract: present = missing_index != code; tests/ops_emulation.py
+    restates it, the kernel itself is checked bit-exactly in test_kernels_gpu.py)."""
+    import ops_emulation as E
+    from missm_b200.bank import MISSING_TYPE_INDEX
+    g = torch.Generator().manual_seed(3)
+    keys = ['image', 'depth', 'thermal', 'video', 'audio', 'language', 'unknown_modality']
+    codes = [MISSING_TYPE_INDEX.get(k, -1) for k in keys]
+    for B in (1, 7, 64, 257):
+        mi = torch.randint(0, 7, (B,), generator=g, dtype=torch.int64)
+        _, _, counts = E.compact_mask(mi, codes)
+        assert [int((mi != c).sum()) for c in codes] == counts.tolist()
+    assert codes[-1] == -1      # a modality without a code is never "missing": all samples present
