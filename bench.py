@@ -408,13 +408,14 @@ def run_gpu_arm(a):
     # roofline of the dominant kernel (tcgen05 GEMM): CUDA events around every GEMM launch of one
     # more step on the launching stream (kept out of the headline so the events cost nothing there)
     import ctypes
-    streams_on = model.encoder.tower_streams
+    streams_on, lockstep_on = model.encoder.tower_streams, model.encoder.lockstep
     model.encoder.tower_streams = False       # one stream: every GEMM is timed alone, not overlapped with another tower's
+    model.encoder.lockstep = False            # ... and tower by tower, as the kernels of a tower follow one another
     L.missm_gemm_profile(1)
     step_resident()
     torch.cuda.synchronize()
     L.missm_gemm_profile(0)
-    model.encoder.tower_streams = streams_on
+    model.encoder.tower_streams, model.encoder.lockstep = streams_on, lockstep_on
     g_ms_c, g_flop_c, n_gemm_c = ctypes.c_double(), ctypes.c_double(), ctypes.c_int64()
     L.missm_gemm_profile_read(ctypes.byref(g_ms_c), ctypes.byref(g_flop_c), ctypes.byref(n_gemm_c))
     g_ms, g_flop, n_gemm = g_ms_c.value, g_flop_c.value, n_gemm_c.value

@@ -202,7 +202,7 @@ class LanguageBind(nn.Module):
         # step in gradient-arrival order and launches bucket k+1 only after bucket k: with tower-by-tower issue the
         # buckets of the second and third tower queued behind the FIRST layer of the first tower (ready at the very end
         # of the backward), which left two thirds of the all-reduce exposed after the backward.
-        lockstep = self.lockstep and use_streams
+        lockstep = self.lockstep and len(keys) > 1      # (without streams: same kernels, interleaved on one stream)
 
         def tower(i, key):
             """Generator: the forward of tower i (yields between layers); returns its [B, P] output."""
