@@ -98,6 +98,29 @@ def test_fp32_mode_host_wiring_matches_reference_golden(tiny):
             assert abs(params[n].grad.norm().item() - ref) < 1e-4 * ref, n
 
 
+def test_lockstep_issue_order_does_not_change_results(tiny):
+    """bank.LanguageBind.forward issues the towers one encoder layer at a time in turn (lockstep) or tower by tower
+    (MISSM_LOCKSTEP=0): same kernels, same operands, another order -- outputs and gradients must be identical."""
+    meta = tiny['meta']
+    modal_types = ['language'] + meta['modals']
+    model, cfgs, tcfg = _make(meta, modal_types, 'sum')
+    model.train()
+    data = R.synth_inputs(modal_types, meta['B'], cfgs, tcfg, seed=0)
+    mi = tiny['missing_index']
+    res = {}
+    with E.emulated_fp32_mode():
+        for mode in (True, False):
+            model.encoder.lockstep = mode
+            model.zero_grad(set_to_none=True)
+            logits = model(data, mi)
+            torch.nn.functional.cross_entropy(logits, tiny['labels']).backward()
+            res[mode] = (logits.detach().clone(), {n: p.grad.clone() for n, p in model.named_parameters() if p.grad is not None})
+    assert torch.equal(res[True][0], res[False][0])
+    assert res[True][1].keys() == res[False][1].keys()
+    for n in res[True][1]:
+        assert torch.equal(res[True][1][n], res[False][1][n]), n
+
+
 def test_precision_switch():
     from missm_b200 import autograd as ag
     assert ag.get_precision() == os.environ.get("MISSM_PRECISION", "bf16")
